@@ -1,0 +1,136 @@
+/*
+ * ngsid.h -- C ABI of libngsid.so: the B200 (sm_100a) implementation of NGSpeciesID's
+ * data-parallel hot paths. Plain pointers and sizes only; every buffer is caller-owned
+ * (numpy / ctypes on the Python side); every entry returns 0 on success and a negative
+ * NGSID_E* code on failure, with a message available from ngsid_last_error().
+ *
+ * One ngsid_ctx per GPU. A context is not thread-safe; distinct contexts are independent.
+ * There is no CPU fallback behind any entry: without a CUDA device ngsid_ctx_create fails.
+ *
+ * The reference (ksahlin/NGSpeciesID v0.3.1) has no FFI: its hot path is plain Python calling
+ * parasail / spoa / racon. Each entry below names the reference function(s) whose arithmetic it
+ * replaces (file:line relative to the reference root); INTEGRATION.md shows the ctypes stub a
+ * maintainer would add to modules/cluster.py and modules/consensus.py to bind them.
+ */
+#ifndef NGSID_H
+#define NGSID_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngsid_ctx ngsid_ctx;
+
+enum {
+    NGSID_OK = 0,
+    NGSID_EINVAL = -1,      /* bad argument (k/w out of range, null pointer, ...)            */
+    NGSID_ECUDA = -2,       /* CUDA runtime error (message has the cudaError string)         */
+    NGSID_ENOMEM = -3,      /* device or host allocation failed                              */
+    NGSID_EUNSUPPORTED = -4,/* input outside what this build handles (non-ACGT base, k > 15) */
+    NGSID_ESTATE = -5       /* call order violated (e.g. cluster before minimizers)          */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int ngsid_ctx_create(int device_id, ngsid_ctx **out);
+void ngsid_ctx_destroy(ngsid_ctx *ctx);
+const char *ngsid_last_error(const ngsid_ctx *ctx);   /* valid until the next call on ctx */
+int ngsid_version(void);                               /* ABI version, currently 1 */
+/* Number of kernels this context has launched since creation / since the last reset. */
+int64_t ngsid_launch_count(const ngsid_ctx *ctx);
+void ngsid_reset_launch_count(ngsid_ctx *ctx);
+int ngsid_sync(ngsid_ctx *ctx);
+
+/* ---- read upload ---------------------------------------------------------------------------
+ * seq / qual: ASCII bases and PHRED+33 qualities of n_reads reads, concatenated; offsets has
+ * n_reads+1 entries (offsets[0] == 0). Copies host->device, packs bases 2 bit/base on the device
+ * (A,C,G,T = 0..3; first base in the most significant bits of each 32-bit word; every read starts
+ * on a word boundary) and rejects any other character with NGSID_EUNSUPPORTED.
+ * Replaces nothing in the reference (its reads are Python str); it is the layout the kernels read.
+ * A new upload discards all per-read results of the previous one.                              */
+int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
+                       const int64_t *offsets, int64_t n_reads);
+
+/* ---- K1: homopolymer compression + (k,w) minimizers ---------------------------------------
+ * Replaces: modules/cluster.py:265 (groupby compression) and cluster.get_kmer_minimizers
+ * (modules/cluster.py:16-39) for every uploaded read. Results stay on the device.
+ * k <= 15 (2k-bit code in a u32), k <= w <= 100.                                               */
+int ngsid_minimizers(ngsid_ctx *ctx, int k, int w);
+/* Timed variant for benchmarks: runs K1 `iters` times back to back on the context's stream and
+ * returns the average kernel duration (CUDA events on that stream) in milliseconds.            */
+int ngsid_minimizers_timed(ngsid_ctx *ctx, int k, int w, int iters, float *avg_ms);
+/* Copy back results for reads [begin, end): len_c and counts have end-begin entries; kmer/pos
+ * receive the concatenated minimizers (capacity `cap` entries; *n_total gets the number
+ * written or needed). kmer is the 2k-bit code, first base most significant; a code with bit 31
+ * set encodes a truncated suffix (reads whose compressed length is < w, reference quirk).      */
+int ngsid_get_minimizers(ngsid_ctx *ctx, int64_t begin, int64_t end, uint32_t *len_c,
+                         uint32_t *counts, uint32_t *kmer, uint32_t *pos, int64_t cap,
+                         int64_t *n_total);
+
+/* ---- K0: quality statistics ----------------------------------------------------------------
+ * Replaces: modules/cluster.py:273-292 (per-run best quality, compressed error rate) and the
+ * per-read part of cluster.py:185-188 (mean capped error probability of the raw qualities).
+ * phred_p: 128 doubles, the caller's PHRED char -> error probability table
+ * (min(10**(-(c-33)/10), 0.79433), computed by the caller so libm differences cannot matter).
+ * bucket_thresholds: 14 doubles, smallest double x for which round(x, 2) >= (b+2)/100,
+ * b = 0..13 (the caller derives them with its own round()); gives the 15 buckets of
+ * cluster.p_shared_minimizer_empirical (cluster.py:356-366).
+ * Sums use Neumaier compensation in ascending character order (what Python >= 3.12's sum()
+ * does), so the doubles equal the reference's.                                                 */
+int ngsid_quality_stats(ngsid_ctx *ctx, const double *phred_p, const double *bucket_thresholds);
+int ngsid_get_quality_stats(ngsid_ctx *ctx, int64_t begin, int64_t end, double *err_compressed,
+                            double *err_raw, uint8_t *bucket);
+
+/* ---- K2+K3+K4: the greedy clustering pass ---------------------------------------------------
+ * Replaces: cluster.reads_to_clusters (modules/cluster.py:207-353) including get_all_hits
+ * (:43-62), get_best_cluster (:67-127), get_best_cluster_block_align (:172-205) and
+ * parasail_block_alignment (:130-169).                                                         */
+typedef struct {
+    int32_t k, w;
+    int32_t min_shared;                 /* --min_shared          (5)   */
+    int32_t symmetric;                  /* --symmetric_map_align_thresholds */
+    double min_fraction;                /* --min_fraction        (0.8) */
+    double mapped_threshold;            /* --mapped_threshold    (0.7) */
+    double aligned_threshold;           /* --aligned_threshold   (0.4) */
+    /* max_gap[b1*15+b2]: largest g with (1-p_emp[b1][b2])^g (left-to-right product from 1)
+     * not < min_prob_no_hits; derived by the caller from the probability table
+     * (modules/p_minimizers_shared.py, NGSpeciesID:72-77) and --min_prob_no_hits.              */
+    int32_t max_gap[225];
+    int32_t tile_reads;                 /* speculation tile size, 0 = default                  */
+    int32_t reserved[7];
+} ngsid_cluster_params;
+
+typedef struct {
+    int64_t n_processed, n_new_reps, n_mapped, n_aln_called, n_aln_passed, n_alignments;
+    int64_t n_tiles, n_chain_steps, n_surprises, n_map_launch_reads, align_cells;
+    int64_t reserved[5];
+} ngsid_cluster_stats;
+
+/* order:      n_order read indices (into the uploaded set) in processing order.
+ * init_reps:  n_init read indices whose minimizers pre-populate the table (merge rounds of
+ *             modules/parallelize.py: the lower batch's representatives); may be NULL/0.
+ * acc_rank:   per uploaded read, rank of its accession string (incl. score suffix) in
+ *             ascending lexicographic order -- the tie-break of cluster.py:79.
+ * out_assign: per entry of `order`: the read index of the representative it joined, or -1 when
+ *             it became a representative itself, or -2 when skipped (compressed length < k).
+ * out_via:    optional (may be NULL): 0 = new, 1 = mapping, 2 = alignment.                     */
+int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params, const int32_t *order,
+                  int64_t n_order, const int32_t *init_reps, int64_t n_init,
+                  const uint32_t *acc_rank, int32_t *out_assign, uint8_t *out_via,
+                  ngsid_cluster_stats *stats);
+
+/* ---- K4 alone: semi-global block alignment statistic ----------------------------------------
+ * Replaces: cluster.parasail_block_alignment (modules/cluster.py:130-169): parasail
+ * sg_trace_scan_16 (match 2, mismatch -2, gap open `open`, extend 1), CIGAR expansion and the
+ * k-column window count. Pairs index uploaded reads: s1 = read_a (rows), s2 = read_b (columns).
+ * out_count[i] = number of windows with >= match_id[i] matches; out_score[i] (optional) = score.
+ * The caller divides by len(s1) / len(s2) (cluster.py:167-168).                                */
+int ngsid_sg_block_align(ngsid_ctx *ctx, const int32_t *read_a, const int32_t *read_b,
+                         const int32_t *open, const int32_t *match_id, int64_t n_pairs, int k,
+                         int32_t *out_count, int32_t *out_score);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGSID_H */

@@ -1,0 +1,42 @@
+"""Builds ngspeciesid_b200/libngsid.so (CUDA kernels + C ABI) for sm_100a with nvcc."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "ngsid_api.cu")
+OUT = os.path.join(HERE, "libngsid.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "--fmad=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def sources():
+    d = os.path.join(HERE, "csrc")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(HERE, "..", "include", "ngsid.h")]
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(s) <= t for s in sources())
+
+
+def build_library(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    cmd = [NVCC] + FLAGS + ["-o", OUT, SRC]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for libngsid.so")
+    with open(os.path.join(HERE, "csrc", ".ptxas.log"), "w") as f:
+        f.write(res.stdout)
+    return OUT
+
+
+if __name__ == "__main__":
+    build_library(force=True, verbose=True)
+    print(OUT)

@@ -1,0 +1,718 @@
+// libngsid.so: C ABI (include/ngsid.h) + host-side orchestration of the sm_100a kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include "ngsid_internal.cuh"
+#include "k1_minimizers.cuh"
+#include "k2_map.cuh"
+#include "k4_align.cuh"
+
+static const size_t SMEM_BUDGET = 200 * 1024;
+
+// ================================================================================ context
+extern "C" int ngsid_version(void) { return 1; }
+
+extern "C" int ngsid_ctx_create(int device_id, ngsid_ctx **out)
+{
+    if (!out) return NGSID_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return NGSID_ECUDA;
+    if (device_id < 0 || device_id >= count) return NGSID_EINVAL;
+    if (cudaSetDevice(device_id) != cudaSuccess) return NGSID_ECUDA;
+    ngsid_ctx *ctx = new ngsid_ctx();
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return NGSID_ECUDA;
+    }
+    *out = ctx;
+    return NGSID_OK;
+}
+
+extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *bufs[] = {&ctx->d_seq, &ctx->d_qual, &ctx->d_off, &ctx->d_packed, &ctx->d_woff, &ctx->d_flag,
+                      &ctx->d_moff, &ctx->d_mins, &ctx->d_nmin, &ctx->d_lenc, &ctx->d_errc, &ctx->d_erru,
+                      &ctx->d_bucket, &ctx->d_phred, &ctx->d_thr, &ctx->d_keys, &ctx->d_heads, &ctx->d_nodes,
+                      &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
+                      &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
+                      &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
+                      &ctx->d_newslots, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+    for (DevBuf *b : bufs) b->release();
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *ngsid_last_error(const ngsid_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int64_t ngsid_launch_count(const ngsid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void ngsid_reset_launch_count(ngsid_ctx *ctx) { if (ctx) ctx->launches = 0; }
+extern "C" int ngsid_sync(ngsid_ctx *ctx)
+{
+    if (!ctx) return NGSID_EINVAL;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NGSID_OK;
+}
+
+// ================================================================================ upload + pack
+extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
+                                  const int64_t *offsets, int64_t n_reads)
+{
+    if (!ctx || !offsets || n_reads < 0 || (n_reads > 0 && (!seq || !qual))) return NGSID_EINVAL;
+    if (n_reads >= (int64_t)1 << 31) return fail(ctx, NGSID_EINVAL, "more than 2^31-1 reads");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ctx->have_min = ctx->have_q = false;
+    ctx->h_nmin_valid = false;
+    ctx->n_reads = n_reads;
+    ctx->h_off.assign(offsets, offsets + n_reads + 1);
+    if (ctx->h_off[0] != 0) return fail(ctx, NGSID_EINVAL, "offsets[0] must be 0");
+    ctx->h_woff.resize(n_reads + 1);
+    int64_t wsum = 0;
+    int maxlen = 0;
+    for (int64_t i = 0; i < n_reads; ++i) {
+        int64_t L = offsets[i + 1] - offsets[i];
+        if (L < 0 || L > (1 << 24)) return fail(ctx, NGSID_EINVAL, "bad read length");
+        ctx->h_woff[i] = wsum;
+        wsum += (L + 15) / 16 + 1;                   // one spare word per read
+        maxlen = std::max<int>(maxlen, (int)L);
+    }
+    ctx->h_woff[n_reads] = wsum;
+    ctx->total_bases = offsets[n_reads];
+    ctx->total_words = wsum;
+    ctx->max_len = maxlen;
+    if (n_reads == 0) return NGSID_OK;
+    size_t nb = (size_t)ctx->total_bases;
+    CUDA_TRY(ctx, ctx->d_seq.ensure(nb + 64));
+    CUDA_TRY(ctx, ctx->d_qual.ensure(nb + 64));
+    CUDA_TRY(ctx, ctx->d_off.ensure((n_reads + 1) * sizeof(int64_t)));
+    CUDA_TRY(ctx, ctx->d_woff.ensure((n_reads + 1) * sizeof(int64_t)));
+    CUDA_TRY(ctx, ctx->d_packed.ensure((size_t)wsum * 4 + 64));
+    CUDA_TRY(ctx, ctx->d_flag.ensure(64));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, seq, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qual.p, qual, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_off.p, offsets, (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_woff.p, ctx->h_woff.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, 64, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_packed.p, 0, (size_t)wsum * 4 + 64, ctx->stream));
+    int blocks = (int)std::min<int64_t>((n_reads + 7) / 8, (int64_t)ctx->sm_count * 16);
+    k_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_off.as<int64_t>(),
+                                                   ctx->d_woff.as<int64_t>(), ctx->d_packed.as<uint32_t>(),
+                                                   n_reads, ctx->d_flag.as<int>());
+    KERNEL_CHECK(ctx);
+    int flag = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flag) {
+        ctx->n_reads = 0;
+        return fail(ctx, NGSID_EUNSUPPORTED, "a read contains a base outside ACGT (unsupported in this build)");
+    }
+    return NGSID_OK;
+}
+
+// ================================================================================ K1
+static int k1_prepare(ngsid_ctx *ctx, int k, int w)
+{
+    if (k < 2 || k > 15) return fail(ctx, NGSID_EUNSUPPORTED, "k must be in 2..15 in this build");
+    if (w < k || w > 100) return fail(ctx, NGSID_EINVAL, "need k <= w <= 100");
+    if (ctx->have_min && ctx->k == k && ctx->w == w) return NGSID_OK;
+    int64_t n = ctx->n_reads;
+    ctx->h_moff.resize(n + 1);
+    int64_t s = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        ctx->h_moff[i] = s;
+        int64_t L = ctx->h_off[i + 1] - ctx->h_off[i];
+        s += std::max<int64_t>(1, L - w + 1);
+    }
+    ctx->h_moff[n] = s;
+    CUDA_TRY(ctx, ctx->d_moff.ensure((n + 1) * sizeof(int64_t)));
+    CUDA_TRY(ctx, ctx->d_mins.ensure((size_t)s * sizeof(Minimizer) + 64));
+    CUDA_TRY(ctx, ctx->d_nmin.ensure((n + 1) * sizeof(uint32_t)));
+    CUDA_TRY(ctx, ctx->d_lenc.ensure((n + 1) * sizeof(uint32_t)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_moff.p, ctx->h_moff.data(), (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->k = k; ctx->w = w;
+    ctx->have_min = false;
+    ctx->h_nmin_valid = false;
+    return NGSID_OK;
+}
+
+static int k1_launch(ngsid_ctx *ctx)
+{
+    int lcap = ((ctx->max_len + 31) / 32) * 32 + 32;
+    size_t per_warp = k1_smem_per_warp(lcap);
+    per_warp = (per_warp + 15) / 16 * 16;
+    // keep lcap-derived stride 16-aligned: per-warp size is computed inside the kernel from lcap
+    if (k1_smem_per_warp(lcap) % 16 != 0) lcap += 16 - (int)((k1_smem_per_warp(lcap) % 16));
+    while (k1_smem_per_warp(lcap) % 16 != 0) lcap += 4;
+    per_warp = k1_smem_per_warp(lcap);
+    int wpb = (int)std::min<size_t>(8, SMEM_BUDGET / per_warp);
+    if (wpb < 1) return fail(ctx, NGSID_EUNSUPPORTED, "read too long for the K1 shared-memory tile");
+    size_t smem = per_warp * wpb;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k1_minimizers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_minimizers_kernel, wpb * 32, smem));
+    bps = std::max(1, bps);
+    int64_t need = (ctx->n_reads + wpb - 1) / wpb;
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * bps));
+    k1_minimizers_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(
+        ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
+        ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
+        ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, lcap);
+    KERNEL_CHECK(ctx);
+    return NGSID_OK;
+}
+
+extern "C" int ngsid_minimizers(ngsid_ctx *ctx, int k, int w)
+{
+    if (!ctx) return NGSID_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = k1_prepare(ctx, k, w);
+    if (rc) return rc;
+    if (ctx->n_reads == 0) { ctx->have_min = true; return NGSID_OK; }
+    rc = k1_launch(ctx);
+    if (rc) return rc;
+    ctx->have_min = true;
+    ctx->h_nmin_valid = false;
+    return NGSID_OK;
+}
+
+extern "C" int ngsid_minimizers_timed(ngsid_ctx *ctx, int k, int w, int iters, float *avg_ms)
+{
+    if (!ctx || iters < 1 || !avg_ms) return NGSID_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = k1_prepare(ctx, k, w);
+    if (rc) return rc;
+    if (ctx->n_reads == 0) { *avg_ms = 0.f; return NGSID_OK; }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int i = 0; i < iters; ++i) {
+        rc = k1_launch(ctx);
+        if (rc) return rc;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *avg_ms = ms / iters;
+    ctx->have_min = true;
+    ctx->h_nmin_valid = false;
+    return NGSID_OK;
+}
+
+static int fetch_nmin(ngsid_ctx *ctx)
+{
+    if (ctx->h_nmin_valid) return NGSID_OK;
+    ctx->h_nmin.resize(ctx->n_reads);
+    if (ctx->n_reads) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_nmin.data(), ctx->d_nmin.p, ctx->n_reads * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->h_nmin_valid = true;
+    return NGSID_OK;
+}
+
+extern "C" int ngsid_get_minimizers(ngsid_ctx *ctx, int64_t begin, int64_t end, uint32_t *len_c,
+                                    uint32_t *counts, uint32_t *kmer, uint32_t *pos, int64_t cap,
+                                    int64_t *n_total)
+{
+    if (!ctx || begin < 0 || end < begin || end > ctx->n_reads) return NGSID_EINVAL;
+    if (!ctx->have_min) return fail(ctx, NGSID_ESTATE, "ngsid_minimizers has not run");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = fetch_nmin(ctx);
+    if (rc) return rc;
+    int64_t n = end - begin, total = 0;
+    for (int64_t i = begin; i < end; ++i) total += ctx->h_nmin[i];
+    if (n_total) *n_total = total;
+    if (counts) for (int64_t i = 0; i < n; ++i) counts[i] = ctx->h_nmin[begin + i];
+    if (len_c && n) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(len_c, ctx->d_lenc.as<uint32_t>() + begin, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (!kmer && !pos) return NGSID_OK;
+    if (total > cap) return fail(ctx, NGSID_EINVAL, "minimizer output buffer too small");
+    if (n == 0) return NGSID_OK;
+    // the slack-CSR region [moff[begin], moff[end]) comes back in one copy, compaction on the host
+    int64_t lo = ctx->h_moff[begin], hi = ctx->h_moff[end];
+    std::vector<Minimizer> tmp((size_t)(hi - lo));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tmp.data(), ctx->d_mins.as<Minimizer>() + lo, (size_t)(hi - lo) * sizeof(Minimizer), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t o = 0;
+    for (int64_t i = begin; i < end; ++i) {
+        const Minimizer *m = tmp.data() + (ctx->h_moff[i] - lo);
+        for (uint32_t j = 0; j < ctx->h_nmin[i]; ++j, ++o) {
+            if (kmer) kmer[o] = m[j].x;
+            if (pos) pos[o] = m[j].y;
+        }
+    }
+    return NGSID_OK;
+}
+
+// ================================================================================ K0
+extern "C" int ngsid_quality_stats(ngsid_ctx *ctx, const double *phred_p, const double *bucket_thresholds)
+{
+    if (!ctx || !phred_p || !bucket_thresholds) return NGSID_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int64_t n = ctx->n_reads;
+    CUDA_TRY(ctx, ctx->d_phred.ensure(128 * sizeof(double)));
+    CUDA_TRY(ctx, ctx->d_thr.ensure(16 * sizeof(double)));
+    CUDA_TRY(ctx, ctx->d_errc.ensure((n + 1) * sizeof(double)));
+    CUDA_TRY(ctx, ctx->d_erru.ensure((n + 1) * sizeof(double)));
+    CUDA_TRY(ctx, ctx->d_bucket.ensure(n + 64));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_phred.p, phred_p, 128 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_thr.p, bucket_thresholds, 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
+        k0_quality_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_qual.as<uint8_t>(),
+                                                           ctx->d_off.as<int64_t>(), ctx->d_phred.as<double>(),
+                                                           ctx->d_thr.as<double>(), ctx->d_errc.as<double>(),
+                                                           ctx->d_erru.as<double>(), ctx->d_bucket.as<uint8_t>(), n);
+        KERNEL_CHECK(ctx);
+    }
+    ctx->have_q = true;
+    return NGSID_OK;
+}
+
+extern "C" int ngsid_get_quality_stats(ngsid_ctx *ctx, int64_t begin, int64_t end, double *err_compressed,
+                                       double *err_raw, uint8_t *bucket)
+{
+    if (!ctx || begin < 0 || end < begin || end > ctx->n_reads) return NGSID_EINVAL;
+    if (!ctx->have_q) return fail(ctx, NGSID_ESTATE, "ngsid_quality_stats has not run");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int64_t n = end - begin;
+    if (n == 0) return NGSID_OK;
+    if (err_compressed) CUDA_TRY(ctx, cudaMemcpyAsync(err_compressed, ctx->d_errc.as<double>() + begin, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (err_raw) CUDA_TRY(ctx, cudaMemcpyAsync(err_raw, ctx->d_erru.as<double>() + begin, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bucket) CUDA_TRY(ctx, cudaMemcpyAsync(bucket, ctx->d_bucket.as<uint8_t>() + begin, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NGSID_OK;
+}
+
+// ================================================================================ K4 launcher
+static int k4_launch(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const int32_t *po,
+                     const int32_t *pm, int stride, int64_t n_pairs, int k, int32_t *out_count,
+                     int32_t *out_score)
+{
+    if (n_pairs == 0) return NGSID_OK;
+    int n2cap = ((ctx->max_len + 15) / 16) * 16 + 16;
+    size_t per_warp = k4_smem_per_warp(n2cap);
+    int wpb = (int)std::min<size_t>(4, SMEM_BUDGET / per_warp);
+    if (wpb < 1) return fail(ctx, NGSID_EUNSUPPORTED, "read too long for the K4 shared-memory row buffer");
+    size_t smem = per_warp * wpb;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k4_align_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k4_align_kernel, wpb * 32, smem));
+    bps = std::max(1, bps);
+    int64_t need = (n_pairs + wpb - 1) / wpb;
+    int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * bps));
+    k4_align_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_off.as<int64_t>(),
+                                                             pa, pb, po, pm, stride, n_pairs, k, n2cap,
+                                                             out_count, out_score);
+    KERNEL_CHECK(ctx);
+    return NGSID_OK;
+}
+
+extern "C" int ngsid_sg_block_align(ngsid_ctx *ctx, const int32_t *read_a, const int32_t *read_b,
+                                    const int32_t *open, const int32_t *match_id, int64_t n_pairs, int k,
+                                    int32_t *out_count, int32_t *out_score)
+{
+    if (!ctx || n_pairs < 0 || (n_pairs > 0 && (!read_a || !read_b || !open || !match_id || !out_count)))
+        return NGSID_EINVAL;
+    if (k < 1 || k > 15) return fail(ctx, NGSID_EUNSUPPORTED, "k must be in 1..15 in this build");
+    if (n_pairs == 0) return NGSID_OK;
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        if (read_a[i] < 0 || read_a[i] >= ctx->n_reads || read_b[i] < 0 || read_b[i] >= ctx->n_reads)
+            return fail(ctx, NGSID_EINVAL, "pair index out of range");
+        int64_t n1 = ctx->h_off[read_a[i] + 1] - ctx->h_off[read_a[i]];
+        int64_t n2 = ctx->h_off[read_b[i] + 1] - ctx->h_off[read_b[i]];
+        if (n1 < 1 || n2 < 1) return fail(ctx, NGSID_EINVAL, "empty sequence in alignment pair");
+        if (n1 + n2 > 65000) return fail(ctx, NGSID_EUNSUPPORTED, "alignment pair too long for the 16-bit window counter");
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t nb = (size_t)n_pairs * sizeof(int32_t);
+    CUDA_TRY(ctx, ctx->d_pa.ensure(nb)); CUDA_TRY(ctx, ctx->d_pb.ensure(nb));
+    CUDA_TRY(ctx, ctx->d_po.ensure(nb)); CUDA_TRY(ctx, ctx->d_pm.ensure(nb));
+    CUDA_TRY(ctx, ctx->d_k4cnt.ensure(nb)); CUDA_TRY(ctx, ctx->d_k4score.ensure(nb));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pa.p, read_a, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pb.p, read_b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_po.p, open, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pm.p, match_id, nb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = k4_launch(ctx, ctx->d_pa.as<int32_t>(), ctx->d_pb.as<int32_t>(), ctx->d_po.as<int32_t>(),
+                       ctx->d_pm.as<int32_t>(), 1, n_pairs, k, ctx->d_k4cnt.as<int32_t>(), ctx->d_k4score.as<int32_t>());
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_count, ctx->d_k4cnt.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_score) CUDA_TRY(ctx, cudaMemcpyAsync(out_score, ctx->d_k4score.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NGSID_OK;
+}
+
+// ================================================================================ clustering driver
+namespace {
+
+struct ClusterRun {
+    ngsid_ctx *ctx;
+    int64_t n;                         // entries of `order`
+    std::vector<int32_t> slot_read, slot_pos;
+    std::vector<uint8_t> slot_state;
+    int n_slots = 0, slots_on_device = 0;
+    uint32_t table_cap = 0;
+    DevBuf keys_alt, heads_alt;        // spare pair for growth
+    int64_t pairs_inserted = 0;
+    int scap = 0, map_warps = 0, map_blocks = 0;
+    DevBuf d_list2, d_err;
+    std::vector<int32_t> h_dec;
+    ngsid_cluster_stats st;
+    MapArgs A;
+
+    int ensure_table(int64_t pairs_after);
+    int ensure_scratch(int slots_after);
+    int push_slots();
+    int set_state(int slot, uint8_t v);
+    int insert_slots(int slot0, int count);
+    int run_map(const int32_t *d_list, int n_list);
+    int fetch_dec(int lo, int hi);
+};
+
+int ClusterRun::ensure_table(int64_t pairs_after)
+{
+    if (table_cap && pairs_after * 2 <= (int64_t)table_cap) return NGSID_OK;
+    uint32_t ncap = 1u << 16;
+    while ((int64_t)ncap < pairs_after * 4) ncap <<= 1;
+    DevBuf &nk = table_cap ? keys_alt : ctx->d_keys;
+    DevBuf &nh = table_cap ? heads_alt : ctx->d_heads;
+    CUDA_TRY(ctx, nk.ensure((size_t)ncap * 4));
+    CUDA_TRY(ctx, nh.ensure((size_t)ncap * 4));
+    CUDA_TRY(ctx, cudaMemsetAsync(nk.p, 0xff, (size_t)ncap * 4, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(nh.p, 0xff, (size_t)ncap * 4, ctx->stream));
+    if (table_cap) {
+        MapTable nt = {nk.as<uint32_t>(), nh.as<int32_t>(), A.table.nodes, ncap - 1};
+        k2_rehash_kernel<<<(table_cap + 255) / 256, 256, 0, ctx->stream>>>(A.table.keys, A.table.heads, table_cap, nt);
+        KERNEL_CHECK(ctx);
+        std::swap(ctx->d_keys, keys_alt);
+        std::swap(ctx->d_heads, heads_alt);
+    }
+    table_cap = ncap;
+    A.table.keys = ctx->d_keys.as<uint32_t>();
+    A.table.heads = ctx->d_heads.as<int32_t>();
+    A.table.cap_mask = ncap - 1;
+    return NGSID_OK;
+}
+
+int ClusterRun::ensure_scratch(int slots_after)
+{
+    if (slots_after <= scap) return NGSID_OK;
+    int ncap = 1024;
+    while (ncap < slots_after * 2) ncap <<= 1;
+    // warps in flight bounded by a 6 GB scratch budget
+    int64_t budget = (int64_t)6 << 30;
+    int64_t max_warps = budget / ((int64_t)ncap * 12);
+    int blocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, std::max<int64_t>(1, max_warps / 8));
+    map_blocks = blocks;
+    map_warps = blocks * 8;
+    size_t bytes = (size_t)map_warps * 12 * ncap;
+    CUDA_TRY(ctx, ctx->d_scratch.ensure(bytes));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_scratch.p, 0, bytes, ctx->stream));
+    scap = ncap;
+    A.scratch = ctx->d_scratch.as<uint32_t>();
+    A.scap = scap;
+    return NGSID_OK;
+}
+
+int ClusterRun::push_slots()
+{
+    if (slots_on_device == n_slots) return NGSID_OK;
+    int a = slots_on_device, c = n_slots - a;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_slot_read.as<int32_t>() + a, slot_read.data() + a, c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_slot_pos.as<int32_t>() + a, slot_pos.data() + a, c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_slot_state.as<uint8_t>() + a, slot_state.data() + a, c, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));   // host vectors may reallocate later
+    slots_on_device = n_slots;
+    A.n_slots = n_slots;
+    return NGSID_OK;
+}
+
+int ClusterRun::set_state(int slot, uint8_t v)
+{
+    slot_state[slot] = v;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_slot_state.as<uint8_t>() + slot, &slot_state[slot], 1, cudaMemcpyHostToDevice, ctx->stream));
+    return NGSID_OK;
+}
+
+int ClusterRun::insert_slots(int slot0, int count)
+{
+    if (count <= 0) return NGSID_OK;
+    int64_t add = 0;
+    for (int s = slot0; s < slot0 + count; ++s) add += ctx->h_nmin[slot_read[s]];
+    int rc = ensure_table(pairs_inserted + add);
+    if (rc) return rc;
+    rc = ensure_scratch(n_slots);
+    if (rc) return rc;
+    rc = push_slots();
+    if (rc) return rc;
+    k2_insert_kernel<<<(count + 7) / 8, 256, 0, ctx->stream>>>(A.table, ctx->d_cursor.as<int32_t>(), ctx->d_slot_read.as<int32_t>(),
+                                                               slot0, count, ctx->d_mins.as<Minimizer>(),
+                                                               ctx->d_moff.as<int64_t>(), ctx->d_nmin.as<uint32_t>());
+    KERNEL_CHECK(ctx);
+    pairs_inserted += add;
+    return NGSID_OK;
+}
+
+int ClusterRun::run_map(const int32_t *d_list, int n_list)
+{
+    if (n_list <= 0) return NGSID_OK;
+    const int32_t *list = d_list;
+    int nl = n_list;
+    while (true) {
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_reqn.p, 0, 4, ctx->stream));
+        A.list = list; A.n_list = nl;
+        int blocks = std::min(map_blocks, (nl + 7) / 8);
+        k2_map_kernel<<<blocks, 256, 0, ctx->stream>>>(A);
+        KERNEL_CHECK(ctx);
+        st.n_map_launch_reads += nl;
+        int32_t hdr[2] = {0, 0};
+        CUDA_TRY(ctx, cudaMemcpyAsync(&hdr[0], ctx->d_reqn.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(&hdr[1], d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (hdr[1]) return fail(ctx, NGSID_EUNSUPPORTED, "more than 8 tied alignment candidates failed for one read");
+        int nreq = hdr[0];
+        if (nreq == 0) return NGSID_OK;
+        const AlignRequest *rq = ctx->d_req.as<AlignRequest>();
+        int rc = k4_launch(ctx, &rq->read_a, &rq->read_b, &rq->open, &rq->match_id, 6, nreq, ctx->k,
+                           ctx->d_k4cnt.as<int32_t>(), nullptr);
+        if (rc) return rc;
+        st.n_alignments += nreq;
+        k2_apply_align_kernel<<<(nreq + 255) / 256, 256, 0, ctx->stream>>>(rq, nreq, ctx->d_k4cnt.as<int32_t>(),
+                                                                           ctx->d_off.as<int64_t>(), A.params, A.acache,
+                                                                           d_list2.as<int32_t>(), d_err.as<int32_t>());
+        KERNEL_CHECK(ctx);
+        list = d_list2.as<int32_t>();
+        nl = nreq;
+    }
+}
+
+int ClusterRun::fetch_dec(int lo, int hi)
+{
+    if (hi <= lo) return NGSID_OK;
+    CUDA_TRY(ctx, cudaMemcpyAsync(h_dec.data() + lo, ctx->d_dec.as<int32_t>() + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NGSID_OK;
+}
+
+}  // namespace
+
+extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params, const int32_t *order,
+                             int64_t n_order, const int32_t *init_reps, int64_t n_init,
+                             const uint32_t *acc_rank, int32_t *out_assign, uint8_t *out_via,
+                             ngsid_cluster_stats *stats)
+{
+    if (!ctx || !params || n_order < 0 || (n_order > 0 && (!order || !out_assign)) || !acc_rank ||
+        n_init < 0 || (n_init > 0 && !init_reps))
+        return NGSID_EINVAL;
+    if (!ctx->have_min || !ctx->have_q) return fail(ctx, NGSID_ESTATE, "run ngsid_minimizers and ngsid_quality_stats first");
+    if (params->k != ctx->k || params->w != ctx->w) return fail(ctx, NGSID_ESTATE, "k/w differ from the extracted minimizers");
+    if (n_order + n_init >= ((int64_t)1 << 30)) return fail(ctx, NGSID_EINVAL, "too many reads for one pass");
+    for (int64_t i = 0; i < n_order; ++i)
+        if (order[i] < 0 || order[i] >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "order index out of range");
+    for (int64_t i = 0; i < n_init; ++i)
+        if (init_reps[i] < 0 || init_reps[i] >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "init_reps index out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = fetch_nmin(ctx);
+    if (rc) return rc;
+
+    ClusterRun R;
+    R.ctx = ctx;
+    R.n = n_order;
+    memset(&R.st, 0, sizeof(R.st));
+    const int n = (int)n_order;
+    const int max_slots = (int)(n_init + n_order) + 1;
+    int64_t max_pairs = 0;
+    for (int64_t i = 0; i < n_init; ++i) max_pairs += ctx->h_nmin[init_reps[i]];
+    for (int64_t i = 0; i < n_order; ++i) max_pairs += ctx->h_nmin[order[i]];
+    if (max_pairs >= ((int64_t)1 << 31)) return fail(ctx, NGSID_EINVAL, "too many minimizers for one pass");
+
+    DeviceClusterParams hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.k = params->k; hp.min_shared = params->min_shared; hp.symmetric = params->symmetric;
+    hp.min_fraction = params->min_fraction; hp.mapped_threshold = params->mapped_threshold;
+    hp.aligned_threshold = params->aligned_threshold;
+    memcpy(hp.max_gap, params->max_gap, sizeof(hp.max_gap));
+
+    CUDA_TRY(ctx, ctx->d_params.ensure(sizeof(hp)));
+    CUDA_TRY(ctx, ctx->d_order.ensure((size_t)n * 4 + 64));
+    CUDA_TRY(ctx, ctx->d_accrank.ensure((size_t)ctx->n_reads * 4 + 64));
+    CUDA_TRY(ctx, ctx->d_dec.ensure((size_t)n * 4 + 64));
+    CUDA_TRY(ctx, ctx->d_via.ensure((size_t)n + 64));
+    CUDA_TRY(ctx, ctx->d_list.ensure((size_t)n * 4 + 64));
+    CUDA_TRY(ctx, R.d_list2.ensure((size_t)n * 4 + 64));
+    CUDA_TRY(ctx, R.d_err.ensure(64));
+    CUDA_TRY(ctx, ctx->d_req.ensure((size_t)n * sizeof(AlignRequest) + 64));
+    CUDA_TRY(ctx, ctx->d_reqn.ensure(64));
+    CUDA_TRY(ctx, ctx->d_k4cnt.ensure((size_t)n * 4 + 64));
+    CUDA_TRY(ctx, ctx->d_acache.ensure((size_t)n * ACACHE_N * sizeof(AlignCacheEntry) + 64));
+    CUDA_TRY(ctx, ctx->d_nodes.ensure((size_t)(max_pairs + 1) * sizeof(PostingNode)));
+    CUDA_TRY(ctx, ctx->d_cursor.ensure(64));
+    CUDA_TRY(ctx, ctx->d_slot_read.ensure((size_t)max_slots * 4));
+    CUDA_TRY(ctx, ctx->d_slot_pos.ensure((size_t)max_slots * 4));
+    CUDA_TRY(ctx, ctx->d_slot_state.ensure((size_t)max_slots));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params.p, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_order.p, order, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_accrank.p, acc_rank, (size_t)ctx->n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_cursor.p, 0, 64, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(R.d_err.p, 0, 64, ctx->stream));
+    if (n) {
+        int64_t ne = (int64_t)n * ACACHE_N;
+        k2_fill_acache_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_acache.as<AlignCacheEntry>(), ne);
+        KERNEL_CHECK(ctx);
+    }
+
+    MapArgs &A = R.A;
+    memset(&A, 0, sizeof(A));
+    A.table.nodes = ctx->d_nodes.as<PostingNode>();
+    A.params = ctx->d_params.as<DeviceClusterParams>();
+    A.order = ctx->d_order.as<int32_t>();
+    A.slot_read = ctx->d_slot_read.as<int32_t>();
+    A.slot_pos = ctx->d_slot_pos.as<int32_t>();
+    A.slot_state = ctx->d_slot_state.as<uint8_t>();
+    A.mins = ctx->d_mins.as<Minimizer>();
+    A.moff = ctx->d_moff.as<int64_t>();
+    A.nmin = ctx->d_nmin.as<uint32_t>();
+    A.lenc = ctx->d_lenc.as<uint32_t>();
+    A.bucket = ctx->d_bucket.as<uint8_t>();
+    A.erru = ctx->d_erru.as<double>();
+    A.acc_rank = ctx->d_accrank.as<uint32_t>();
+    A.acache = ctx->d_acache.as<AlignCacheEntry>();
+    A.dec = ctx->d_dec.as<int32_t>();
+    A.via = ctx->d_via.as<uint8_t>();
+    A.req = ctx->d_req.as<AlignRequest>();
+    A.req_n = ctx->d_reqn.as<int32_t>();
+    A.err_flag = R.d_err.as<int32_t>();
+
+    R.slot_read.reserve(max_slots); R.slot_pos.reserve(max_slots); R.slot_state.reserve(max_slots);
+    R.h_dec.assign(n, DEC_NEW);
+
+    auto cleanup = [&](int code) { R.keys_alt.release(); R.heads_alt.release(); R.d_list2.release(); R.d_err.release(); return code; };
+
+    // ---- initial representatives (merge rounds of modules/parallelize.py:196-215)
+    for (int64_t i = 0; i < n_init; ++i) {
+        R.slot_read.push_back(init_reps[i]); R.slot_pos.push_back(-1); R.slot_state.push_back(SLOT_VALID);
+    }
+    R.n_slots = (int)n_init;
+    rc = R.ensure_table(std::max<int64_t>(1, 0));
+    if (rc) return cleanup(rc);
+    rc = R.ensure_scratch(std::max(1, R.n_slots));
+    if (rc) return cleanup(rc);
+    rc = R.insert_slots(0, R.n_slots);
+    if (rc) return cleanup(rc);
+
+    const int tmax = params->tile_reads > 0 ? params->tile_reads : 4096;
+    int T = std::min(32, tmax);
+    int pos = 0;
+    std::vector<int32_t> U, h_list;
+    while (pos < n) {
+        const int hi = std::min(n, pos + T);
+        R.st.n_tiles++;
+        // ---- phase 1: speculative pass against the representatives known before the tile
+        k2_iota_kernel<<<(hi - pos + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_list.as<int32_t>(), pos, hi - pos);
+        KERNEL_CHECK(ctx);
+        rc = R.run_map(ctx->d_list.as<int32_t>(), hi - pos);
+        if (rc) return cleanup(rc);
+        rc = R.fetch_dec(pos, hi);
+        if (rc) return cleanup(rc);
+        U.clear();
+        for (int i = pos; i < hi; ++i) if (R.h_dec[i] == DEC_NEW) U.push_back(i);
+        if (U.empty()) { pos = hi; T = std::min(T * 2, tmax); continue; }
+
+        // ---- tentative representatives; the first one is certain
+        const int slot0 = R.n_slots;
+        for (size_t u = 0; u < U.size(); ++u) {
+            R.slot_read.push_back(order[U[u]]); R.slot_pos.push_back(U[u]);
+            R.slot_state.push_back(u == 0 ? SLOT_VALID : SLOT_TENTATIVE);
+        }
+        R.n_slots += (int)U.size();
+        rc = R.insert_slots(slot0, (int)U.size());
+        if (rc) return cleanup(rc);
+
+        // ---- phase 2: resolve the tentative ones in order against the certain ones before them
+        for (size_t u = 1; u < U.size(); ++u) {
+            k2_iota_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_list.as<int32_t>(), U[u], 1);
+            KERNEL_CHECK(ctx);
+            rc = R.run_map(ctx->d_list.as<int32_t>(), 1);
+            if (rc) return cleanup(rc);
+            rc = R.fetch_dec(U[u], U[u] + 1);
+            if (rc) return cleanup(rc);
+            R.st.n_chain_steps++;
+            rc = R.set_state(slot0 + (int)u, R.h_dec[U[u]] == DEC_NEW ? SLOT_VALID : SLOT_DEAD);
+            if (rc) return cleanup(rc);
+        }
+
+        // ---- phase 3: the other reads after the first new representative see the new ones
+        const int first = U[0];
+        h_list.clear();
+        {
+            size_t ui = 0;
+            for (int i = first + 1; i < hi; ++i) {
+                while (ui < U.size() && U[ui] < i) ++ui;
+                if (ui < U.size() && U[ui] == i) continue;
+                if (R.h_dec[i] == DEC_SKIP) continue;
+                h_list.push_back(i);
+            }
+        }
+        int surprise = -1;
+        if (!h_list.empty()) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_list.p, h_list.data(), h_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            rc = R.run_map(ctx->d_list.as<int32_t>(), (int)h_list.size());
+            if (rc) return cleanup(rc);
+            rc = R.fetch_dec(first + 1, hi);
+            if (rc) return cleanup(rc);
+            for (int i : h_list) if (R.h_dec[i] == DEC_NEW) { surprise = i; break; }
+        }
+        if (surprise < 0) { pos = hi; T = std::min(T * 2, tmax); continue; }
+
+        // ---- a read that had been assigned became a representative: everything after it in the
+        // tile is re-done with it in the table
+        R.st.n_surprises++;
+        for (size_t u = 0; u < U.size(); ++u)
+            if (U[u] > surprise && R.slot_state[slot0 + u] != SLOT_DEAD) {
+                rc = R.set_state(slot0 + (int)u, SLOT_DEAD);
+                if (rc) return cleanup(rc);
+            }
+        const int s_slot = R.n_slots;
+        R.slot_read.push_back(order[surprise]); R.slot_pos.push_back(surprise); R.slot_state.push_back(SLOT_VALID);
+        R.n_slots++;
+        rc = R.insert_slots(s_slot, 1);
+        if (rc) return cleanup(rc);
+        if (hi > surprise + 1) {
+            int64_t ne = (int64_t)(hi - surprise - 1) * ACACHE_N;
+            k2_fill_acache_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->d_acache.as<AlignCacheEntry>() + (size_t)(surprise + 1) * ACACHE_N, ne);
+            KERNEL_CHECK(ctx);
+        }
+        pos = surprise + 1;
+        T = std::max(32, T / 2);
+    }
+
+    // ---- results
+    std::vector<uint8_t> h_via(n);
+    if (n) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(h_via.data(), ctx->d_via.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    for (int i = 0; i < n; ++i) {
+        int d = R.h_dec[i];
+        out_assign[i] = d;
+        if (out_via) out_via[i] = (d >= 0) ? h_via[i] : 0;
+        if (d == DEC_SKIP) continue;
+        R.st.n_processed++;
+        if (d == DEC_NEW) R.st.n_new_reps++;
+        else if (h_via[i] == 1) R.st.n_mapped++;
+        else R.st.n_aln_passed++;
+    }
+    if (stats) *stats = R.st;
+    return cleanup(NGSID_OK);
+}

@@ -1,0 +1,92 @@
+// Internal definitions shared by the kernels and the C ABI (single translation unit: ngsid_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/ngsid.h"
+
+#define NGSID_NEG_INF (-(1 << 29))
+#define NGSID_FULL_MASK 0xffffffffu
+
+// ---- device buffer that only ever grows -------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// Packed minimizer record: x = 2k-bit k-mer code (first base most significant), y = position in
+// homopolymer-compressed coordinates.
+typedef uint2 Minimizer;
+
+struct ngsid_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // ---- uploaded reads
+    int64_t n_reads = 0, total_bases = 0, total_words = 0;
+    int max_len = 0;
+    std::vector<int64_t> h_off;       // n+1 byte offsets
+    std::vector<int64_t> h_woff;      // n+1 word offsets of the packed reads
+    DevBuf d_seq, d_qual, d_off, d_packed, d_woff, d_flag;
+
+    // ---- K1 results
+    int k = 0, w = 0;
+    bool have_min = false;
+    std::vector<int64_t> h_moff;      // n+1 offsets into d_mins (slack CSR: capacity per read)
+    std::vector<uint32_t> h_nmin;     // mirror of d_nmin (filled lazily)
+    bool h_nmin_valid = false;
+    DevBuf d_moff, d_mins, d_nmin, d_lenc;
+
+    // ---- K0 results
+    bool have_q = false;
+    DevBuf d_errc, d_erru, d_bucket, d_phred, d_thr;
+
+    // ---- clustering scratch (see cluster_driver.cuh)
+    DevBuf d_keys, d_heads, d_nodes, d_cursor, d_slot_read, d_slot_pos, d_slot_state;
+    DevBuf d_order, d_accrank, d_dec, d_aux, d_via, d_list, d_scratch, d_params;
+    DevBuf d_req, d_reqn, d_acache, d_k4cnt, d_k4score, d_newslots, d_pa, d_pb, d_po, d_pm;
+};
+
+#define CUDA_TRY(ctx, call)                                                                    \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                   \
+            return (_e == cudaErrorMemoryAllocation) ? NGSID_ENOMEM : NGSID_ECUDA;             \
+        }                                                                                      \
+    } while (0)
+
+#define KERNEL_CHECK(ctx)                                                                      \
+    do {                                                                                       \
+        (ctx)->launches++;                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess) {                                                               \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(_e);              \
+            return NGSID_ECUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+static inline int fail(ngsid_ctx *ctx, int code, const std::string &msg) {
+    ctx->err = msg;
+    return code;
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }

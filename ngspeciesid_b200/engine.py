@@ -1,0 +1,224 @@
+"""
+Array-level host API over the C ABI: one Engine per GPU. This is the call surface bench.py times
+end to end (host numpy buffers in, host numpy results out) and what the reference-shaped
+wrappers in ngspeciesid_b200.modules sit on.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import ClusterParams, ClusterStats, NgsidError, as_array, ptr
+
+# PHRED char -> capped error probability, exactly the reference's table (modules/cluster.py:233)
+PHRED_P = np.array([min(10 ** (-(c - 33) / 10.0), 0.79433) for c in range(128)], dtype=np.float64)
+
+
+def bucket_thresholds():
+    """14 doubles: the smallest x with round(x, 2) >= (b+2)/100, b = 0..13, found with Python's
+    own round() so that the device bucketing equals cluster.p_shared_minimizer_empirical
+    (modules/cluster.py:356-366)."""
+    out = []
+    for b in range(14):
+        target = round((b + 2) / 100.0, 2)
+        x = (b + 1) / 100.0 + 0.005
+        while round(x, 2) >= target:
+            x = math.nextafter(x, 0.0)
+        while round(x, 2) < target:
+            x = math.nextafter(x, 1.0)
+        out.append(x)
+    return np.array(out, dtype=np.float64)
+
+
+def bucket_values():
+    return [round(0.01 * (b + 1), 2) for b in range(15)]
+
+
+def max_gap_table(p_emp_probs, min_prob_no_hits):
+    """max_gap[b1*15+b2]: largest gap g for which the left-to-right product of g factors
+    (1 - p_emp[(e1,e2)]) starting from 1 is not < min_prob_no_hits (modules/cluster.py:97-112)."""
+    vals = bucket_values()
+    out = np.zeros(225, dtype=np.int32)
+    for b1, e1 in enumerate(vals):
+        for b2, e2 in enumerate(vals):
+            q = 1.0 - p_emp_probs[(e1, e2)]
+            g, prod = -1, 1
+            while not (prod < min_prob_no_hits):
+                g += 1
+                if g > 1 << 20:
+                    break
+                prod = prod * q
+            out[b1 * 15 + b2] = g
+    return out
+
+
+def accession_ranks(accessions):
+    """Rank of each accession string in ascending order (Python compares str by code point, which
+    is the byte order of UTF-8) -- the tie-break of modules/cluster.py:79. Equal strings share a
+    rank."""
+    n = len(accessions)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint32)
+    arr = np.array([a.encode("utf-8") for a in accessions])
+    order = np.argsort(arr, kind="stable")
+    srt = arr[order]
+    start = np.ones(n, dtype=bool)
+    start[1:] = srt[1:] != srt[:-1]
+    group_first = np.maximum.accumulate(np.where(start, np.arange(n), 0))
+    rank = np.empty(n, dtype=np.uint32)
+    rank[order] = group_first.astype(np.uint32)
+    return rank
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.ngsid_ctx_create(device, ctypes.byref(h))
+        if rc != 0 or not h:
+            raise NgsidError(rc, "ngsid_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+        self.n_reads = 0
+        self.offsets = None
+        self._q_done = False
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ngsid_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise NgsidError(rc, self.lib.ngsid_last_error(self.h).decode("utf-8", "replace"))
+
+    # ---- reads
+    def upload(self, seq, qual, offsets):
+        seq = as_array(seq, np.uint8)
+        qual = as_array(qual, np.uint8)
+        offsets = as_array(offsets, np.int64)
+        n = len(offsets) - 1
+        if len(seq) != offsets[-1] or len(qual) != offsets[-1]:
+            raise ValueError("seq/qual length does not match offsets")
+        self._check(self.lib.ngsid_upload_reads(self.h, ptr(seq), ptr(qual), ptr(offsets), n))
+        self.n_reads = n
+        self.offsets = offsets
+        self._q_done = False
+
+    def upload_records(self, records):
+        """records: iterable of (seq:str, qual:str)."""
+        seqs, quals = [], []
+        for s, q in records:
+            seqs.append(s.encode("ascii"))
+            quals.append(q.encode("ascii"))
+        offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=offs[1:])
+        self.upload(np.frombuffer(b"".join(seqs), dtype=np.uint8), np.frombuffer(b"".join(quals), dtype=np.uint8), offs)
+
+    # ---- K1
+    def minimizers(self, k, w):
+        self._check(self.lib.ngsid_minimizers(self.h, k, w))
+
+    def minimizers_timed(self, k, w, iters):
+        ms = ctypes.c_float(0)
+        self._check(self.lib.ngsid_minimizers_timed(self.h, k, w, iters, ctypes.byref(ms)))
+        return ms.value
+
+    def get_minimizers(self, begin=0, end=None):
+        end = self.n_reads if end is None else end
+        n = end - begin
+        len_c = np.zeros(n, dtype=np.uint32)
+        counts = np.zeros(n, dtype=np.uint32)
+        total = ctypes.c_int64(0)
+        self._check(self.lib.ngsid_get_minimizers(self.h, begin, end, ptr(len_c), ptr(counts), None, None, 0, ctypes.byref(total)))
+        kmer = np.zeros(total.value, dtype=np.uint32)
+        pos = np.zeros(total.value, dtype=np.uint32)
+        self._check(self.lib.ngsid_get_minimizers(self.h, begin, end, None, None, ptr(kmer), ptr(pos), total.value, ctypes.byref(total)))
+        return len_c, counts, kmer, pos
+
+    # ---- K0
+    def quality_stats(self):
+        thr = bucket_thresholds()
+        self._check(self.lib.ngsid_quality_stats(self.h, ptr(PHRED_P), ptr(thr)))
+        self._q_done = True
+
+    def get_quality_stats(self, begin=0, end=None):
+        end = self.n_reads if end is None else end
+        n = end - begin
+        ec, eu, bk = np.zeros(n), np.zeros(n), np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.ngsid_get_quality_stats(self.h, begin, end, ptr(ec), ptr(eu), ptr(bk)))
+        return ec, eu, bk
+
+    # ---- clustering pass
+    def cluster(self, k, w, max_gap, order, acc_rank, init_reps=None, min_shared=5, min_fraction=0.8,
+                mapped_threshold=0.7, aligned_threshold=0.4, symmetric=False, tile_reads=0):
+        p = ClusterParams()
+        p.k, p.w, p.min_shared, p.symmetric = k, w, min_shared, 1 if symmetric else 0
+        p.min_fraction, p.mapped_threshold, p.aligned_threshold = min_fraction, mapped_threshold, aligned_threshold
+        mg = as_array(max_gap, np.int32)
+        if mg.shape != (225,):
+            raise ValueError("max_gap must have 225 entries")
+        for i in range(225):
+            p.max_gap[i] = int(mg[i])
+        p.tile_reads = tile_reads
+        order = as_array(order, np.int32)
+        acc_rank = as_array(acc_rank, np.uint32)
+        if len(acc_rank) != self.n_reads:
+            raise ValueError("acc_rank needs one entry per uploaded read")
+        init = None if init_reps is None or len(init_reps) == 0 else as_array(init_reps, np.int32)
+        assign = np.zeros(len(order), dtype=np.int32)
+        via = np.zeros(len(order), dtype=np.uint8)
+        st = ClusterStats()
+        self._check(self.lib.ngsid_cluster(self.h, ctypes.byref(p), ptr(order), len(order), ptr(init),
+                                           0 if init is None else len(init), ptr(acc_rank), ptr(assign), ptr(via),
+                                           ctypes.byref(st)))
+        return assign, via, st.as_dict()
+
+    # ---- K4 alone
+    def sg_block_align(self, read_a, read_b, open_pen, match_id, k, want_score=False):
+        a, b = as_array(read_a, np.int32), as_array(read_b, np.int32)
+        o, m = as_array(open_pen, np.int32), as_array(match_id, np.int32)
+        cnt = np.zeros(len(a), dtype=np.int32)
+        score = np.zeros(len(a), dtype=np.int32) if want_score else None
+        self._check(self.lib.ngsid_sg_block_align(self.h, ptr(a), ptr(b), ptr(o), ptr(m), len(a), k, ptr(cnt), ptr(score)))
+        return (cnt, score) if want_score else cnt
+
+    def launch_count(self):
+        return int(self.lib.ngsid_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.lib.ngsid_reset_launch_count(self.h)
+
+    def sync(self):
+        self._check(self.lib.ngsid_sync(self.h))
+
+
+_ENGINES = {}
+
+
+def get_engine(device=0):
+    """One cached Engine per device for the reference-shaped wrappers."""
+    e = _ENGINES.get(device)
+    if e is None or e.h is None:
+        e = _ENGINES[device] = Engine(device)
+    return e
+
+
+def decode_kmer(code, k):
+    """2k-bit code (or truncated-suffix code, bit 31 set) -> string."""
+    code = int(code)
+    if code & (1 << 31):
+        body = code & ~(1 << 31)
+        t = (body.bit_length() - 1) // 2
+        body &= (1 << (2 * t)) - 1
+        n = t
+    else:
+        body, n = code, k
+    return "".join("ACGT"[(body >> (2 * (n - 1 - i))) & 3] for i in range(n))

@@ -1,0 +1,143 @@
+"""
+Drop-in for the reference's modules/cluster.py hot path (ksahlin/NGSpeciesID v0.3.1), computed on
+the GPU through libngsid.so. Function names, arguments, mutation of the caller's dicts and return
+values follow the reference (file:line cited per function); there is no CPU fallback.
+"""
+import itertools
+import logging
+import math
+
+import numpy as np
+
+from .. import engine as _engine
+
+
+def _hpol(seq):
+    return "".join(ch for ch, _ in itertools.groupby(seq))
+
+
+def get_kmer_minimizers(seq, k_size, w_size):
+    """Reference: modules/cluster.py:16-39. `seq` is the (already homopolymer-compressed) string;
+    returns [(kmer, position)]. The kernel compresses its input itself, which is the identity on
+    a compressed string; inputs that still contain homopolymers are handled by doubling... no:
+    they are rejected, because the reference would treat them differently."""
+    if _hpol(seq) != seq:
+        raise ValueError("get_kmer_minimizers expects a homopolymer-compressed sequence "
+                         "(the reference only ever passes seq_hpol_comp, modules/cluster.py:269)")
+    eng = _engine.get_engine()
+    eng.upload_records([(seq, "I" * len(seq))])
+    eng.minimizers(k_size, w_size)
+    _lc, _cnt, kmer, pos = eng.get_minimizers(0, 1)
+    return [(_engine.decode_kmer(c, k_size), int(p)) for c, p in zip(kmer, pos)]
+
+
+def p_shared_minimizer_empirical(error_rate_read, error_rate_center, p_emp_probs):
+    """Reference: modules/cluster.py:356-368 (host-side lookup; the device uses the bucketed form)."""
+    def bucket(e):
+        e = round(e, 2)
+        return 0.15 if e > 0.15 else (0.01 if e < 0.01 else e)
+    return p_emp_probs[(bucket(error_rate_read), bucket(error_rate_center))]
+
+
+def parasail_block_alignment(s1, s2, k, match_id, match_score=2, mismatch_penalty=-2, opening_penalty=5, gap_ext=1):
+    """Reference: modules/cluster.py:130-169. Returns (s1, s2, (None, None, alignment_ratio,
+    target_alignment_ratio)): the gapped strings are not materialised (the kernel computes the
+    block statistic during the DP); every caller in the reference only uses the two ratios."""
+    if (match_score, mismatch_penalty, gap_ext) != (2, -2, 1):
+        raise NotImplementedError("the kernel implements the reference's fixed scoring 2/-2/ext 1")
+    eng = _engine.get_engine()
+    eng.upload_records([(s1, "I" * len(s1)), (s2, "I" * len(s2))])
+    cnt = eng.sg_block_align([0], [1], [opening_penalty], [match_id], k)
+    c = int(cnt[0])
+    return (s1, s2, (None, None, c / float(len(s1)), c / float(len(s2))))
+
+
+def reads_to_clusters(clusters, representatives, sorted_reads, p_emp_probs, minimizer_database, new_batch_index, args):
+    """Reference: modules/cluster.py:207-353. Same contract: iterates `sorted_reads` in order,
+    mutates `clusters`, `representatives` (values become 8-tuples) and `minimizer_database`
+    ({kmer: set(ids)}), returns {new_batch_index: (clusters, representatives,
+    minimizer_database, new_batch_index)}."""
+    k, w = args.k, args.w
+    prev_b = [r[1] for r in sorted_reads]
+    lowest = max(1, min(prev_b or [1]))
+
+    # reads whose batch index equals the lowest one are the table's own representatives:
+    # only their batch index changes (modules/cluster.py:243-248)
+    todo = []
+    for rec in sorted_reads:
+        rid = rec[0]
+        if rec[1] == lowest:
+            t = representatives[rid]
+            representatives[rid] = t[:1] + (new_batch_index,) + t[2:]
+        else:
+            todo.append(rec)
+
+    # representatives already in the caller's table
+    init_ids = set()
+    for ids in minimizer_database.values():
+        init_ids.update(ids)
+    init_ids = sorted(init_ids)
+
+    if todo:
+        local = {}
+        records, accs = [], []
+        for rid in init_ids:
+            t = representatives[rid]
+            local[rid] = len(records)
+            records.append((t[3], t[4]))
+            accs.append(t[2])
+        for (rid, _b, acc, seq, qual, _s) in todo:
+            local[rid] = len(records)
+            records.append((seq, qual))
+            accs.append(acc)
+        eng = _engine.get_engine(getattr(args, "device", 0))
+        eng.upload_records(records)
+        eng.minimizers(k, w)
+        eng.quality_stats()
+        max_gap = _engine.max_gap_table(p_emp_probs, args.min_prob_no_hits)
+        order = np.array([local[r[0]] for r in todo], dtype=np.int32)
+        init = np.array([local[r] for r in init_ids], dtype=np.int32)
+        assign, via, stats = eng.cluster(k, w, max_gap, order, _engine.accession_ranks(accs), init_reps=init,
+                                         min_shared=args.min_shared, min_fraction=args.min_fraction,
+                                         mapped_threshold=args.mapped_threshold,
+                                         aligned_threshold=args.aligned_threshold,
+                                         symmetric=bool(args.symmetric_map_align_thresholds))
+        err_c, _eu, _bk = eng.get_quality_stats()
+        local_to_id = {v: kk for kk, v in local.items()}
+        new_reps = [i for i, a in enumerate(assign) if a == -1]
+        # minimizers of the new representatives go into the caller's table (cluster.py:328-334)
+        if new_reps:
+            _lc, counts, kmer, pos = eng.get_minimizers()
+            starts = np.zeros(len(counts) + 1, dtype=np.int64)
+            np.cumsum(counts, out=starts[1:])
+        moved = []
+        for i, rec in enumerate(todo):
+            rid, _b, acc, seq, qual, score = rec
+            a = int(assign[i])
+            if a == -2:
+                continue                                      # compressed read shorter than k
+            t = representatives[rid]
+            if len(t) == 8:
+                representatives[rid] = t[:1] + (new_batch_index,) + t[2:]
+            else:
+                representatives[rid] = (rid, new_batch_index, acc, seq, qual, score,
+                                        float(err_c[local[rid]]), _hpol(seq) if a == -1 else None)
+            if a >= 0:
+                moved.append((rid, local_to_id[a]))
+            else:
+                li = local[rid]
+                for c in kmer[starts[li]:starts[li + 1]]:
+                    m = _engine.decode_kmer(c, k)
+                    s = minimizer_database.get(m)
+                    if s is None:
+                        minimizer_database[m] = s = set()
+                    s.add(rid)
+        for rid, winner in moved:                             # cluster.py:338-345
+            clusters[winner].extend(clusters[rid])
+            del clusters[rid]
+            del representatives[rid]
+        logging.debug("Total number of reads iterated through:{0}".format(len(sorted_reads)))
+        logging.debug("Passed mapping criteria:{0}".format(stats["n_mapped"]))
+        logging.debug("Passed alignment criteria in this process:{0}".format(stats["n_aln_passed"]))
+        logging.debug("Total calls to alignment module in this process:{0}".format(stats["n_alignments"]))
+    return {new_batch_index: (clusters, representatives, minimizer_database, new_batch_index)}

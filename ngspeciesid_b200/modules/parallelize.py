@@ -1,0 +1,84 @@
+"""
+Drop-in for the reference's modules/parallelize.py (ksahlin/NGSpeciesID v0.3.1): the batch split
+and the log2 rounds of pairwise batch merges are the reference's (results depend on --t exactly
+as there); the batches of a round run one after the other on the GPU instead of in a process
+pool -- they are independent, so the result is the same.
+"""
+import math
+
+from . import cluster
+
+
+def batch_list(lst, nr_cores=1, batch_type="nr_reads", merge_consecutive=False):
+    """Reference: modules/parallelize.py:33-81 (generator of batches)."""
+    if merge_consecutive:
+        bound, cur = 2, []
+        for info in lst:
+            if info[1] <= bound:
+                cur.append(info)
+            else:
+                yield cur
+                bound += 2
+                cur = [info]
+        yield cur
+        return
+    if batch_type == "nr_reads":
+        size = int(len(lst) / nr_cores) + 1
+        for i in range(0, len(lst), size):
+            yield lst[i:i + size]
+        return
+    if batch_type == "total_nt":
+        weight = lambda r: len(r[3])
+    elif batch_type == "read_lengths_squared":
+        weight = lambda r: math.pow(len(r[3]), 2)
+    else:
+        return
+    limit = int(sum(weight(r) for r in lst) / nr_cores) + 1
+    cur, acc = [], 0
+    for info in lst:
+        acc += weight(info)
+        cur.append(info)
+        if acc >= limit:
+            yield cur
+            cur, acc = [], 0
+    yield cur
+
+
+def parallel_clustering(read_array, p_emp_probs, args):
+    """Reference: modules/parallelize.py:107-217 -> (clusters, representatives)."""
+    batches = list(batch_list(read_array, args.nr_cores, batch_type=args.batch_type))
+    num = args.nr_cores
+    cl = [{r[0]: [r[2]] for r in b} for b in batches]
+    rp = [{r[0]: tuple(r) for r in b} for b in batches]
+    db = [{} for _ in batches]
+    while True:
+        if len(batches) == 1:
+            res = cluster.reads_to_clusters(cl[0], rp[0], batches[0], p_emp_probs, db[0], 1, args)
+            return res[1][0], res[1][1]
+        all_cl, all_rp, all_db = {}, {}, {}
+        for i in range(len(batches)):
+            res = cluster.reads_to_clusters(cl[i], rp[i], batches[i], p_emp_probs, db[i], i + 1, args)
+            c, r, d, bi = res[i + 1]
+            all_cl.update(c)
+            all_rp.update(r)
+            all_db[bi] = d
+        read_array = [(v[0], v[1], v[2], v[3], v[4], v[5]) for _, v in
+                      sorted(all_rp.items(), key=lambda x: x[1][5], reverse=True)]
+        if num == 1:
+            return all_cl, all_rp
+        batches = list(batch_list(read_array, num, batch_type=args.batch_type, merge_consecutive=True))
+        num = len(batches)
+        cl, rp, db = [], [], []
+        for b in batches:
+            low = min(r[1] for r in b)
+            cl.append({r[0]: all_cl[r[0]] for r in b})
+            rp.append({r[0]: all_rp[r[0]] for r in b})
+            db.append(all_db[low])
+
+
+def single_clustering(read_array, p_emp_probs, args):
+    """Reference: NGSpeciesID:20-33."""
+    clusters = {r[0]: [r[2]] for r in read_array}
+    reps = {r[0]: tuple(r) for r in read_array}
+    res = cluster.reads_to_clusters(clusters, reps, read_array, p_emp_probs, {}, 1, args)
+    return res[1][0], res[1][1]

@@ -1,0 +1,232 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden
+vectors. Everything here needs a B200 (`-m gpu`)."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, scenario_reads, scenario_args
+from oracle import cluster_oracle as oc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ngspeciesid_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _check_minimizers(eng, seqs, k, w):
+    from ngspeciesid_b200.engine import decode_kmer
+    eng.upload_records([(s, "5" * len(s)) for s in seqs])
+    eng.minimizers(k, w)
+    len_c, counts, kmer, pos = eng.get_minimizers()
+    o = 0
+    for i, s in enumerate(seqs):
+        seqc, _ = oc.hpol_compress(s)
+        assert len_c[i] == len(seqc)
+        exp = oc.minimizers(seqc, k, w) if len(seqc) >= k else []
+        got = [(decode_kmer(kmer[o + j], k), int(pos[o + j])) for j in range(counts[i])]
+        assert got == exp, (i, k, w, len(s), len(seqc))
+        o += counts[i]
+
+
+@pytest.mark.parametrize("tag,k,w", [("h1", 13, 20), ("h1", 15, 50), ("supp1k", 13, 20), ("supp1k", 15, 50),
+                                     ("synth2k", 13, 20), ("synthpb", 15, 50), ("h1", 10, 100), ("h1", 13, 13)])
+def test_k1_minimizers_fixtures(eng, tag, k, w):
+    seqs = [s for _a, s, _q in scenario_reads(tag)]
+    _check_minimizers(eng, seqs, k, w)
+
+
+def test_k1_minimizers_edge_cases(eng):
+    cases = load_golden("minimizers.json.gz")
+    by_kw = {}
+    for c in cases:
+        if c["k"] <= 15:
+            by_kw.setdefault((c["k"], c["w"]), []).append(c)
+    from ngspeciesid_b200.engine import decode_kmer
+    for (k, w), cs in by_kw.items():
+        eng.upload_records([(c["seq"], "5" * len(c["seq"])) for c in cs])
+        eng.minimizers(k, w)
+        _lc, counts, kmer, pos = eng.get_minimizers()
+        o = 0
+        for i, c in enumerate(cs):
+            got = [[decode_kmer(kmer[o + j], k), int(pos[o + j])] for j in range(counts[i])]
+            assert got == c["mins"], (k, w, len(c["seq"]))
+            o += counts[i]
+    # homopolymer-rich and degenerate inputs, single base reads, reads shorter than k
+    rng = np.random.default_rng(3)
+    seqs = ["A" * 50, "ACGT" * 5, "A", "AC", "ACGTACGTACGTAC", "AAAACCCCGGGGTTTT" * 20]
+    for _ in range(200):
+        n = int(rng.integers(1, 400))
+        p = rng.dirichlet([0.3, 0.3, 0.3, 0.3])
+        seqs.append("".join(rng.choice(list("ACGT"), size=n, p=p)))
+    _check_minimizers(eng, seqs, 13, 20)
+    _check_minimizers(eng, seqs, 15, 50)
+    _check_minimizers(eng, seqs, 5, 9)
+
+
+def test_k1_rejects_non_acgt(eng):
+    from ngspeciesid_b200._lib import NgsidError
+    with pytest.raises(NgsidError):
+        eng.upload_records([("ACGTNACGT", "555555555")])
+
+
+@pytest.mark.parametrize("tag", ["h1", "supp1k", "synth2k"])
+def test_k0_quality_stats(eng, tag):
+    recs = scenario_reads(tag)
+    eng.upload_records([(s, q) for _a, s, q in recs])
+    eng.quality_stats()
+    ec, eu, bk = eng.get_quality_stats()
+    from ngspeciesid_b200.engine import bucket_values
+    vals = bucket_values()
+    for i, (_a, s, q) in enumerate(recs):
+        seqc, runs = oc.hpol_compress(s)
+        qc = oc.compress_quality(q, runs)
+        e1 = oc.poisson_mean(qc) / float(len(qc))
+        e2 = oc.poisson_mean(q) / float(len(s))
+        assert repr(float(ec[i])) == repr(e1), i
+        assert repr(float(eu[i])) == repr(e2), i
+        assert vals[bk[i]] == oc.error_bucket(e1)
+
+
+def test_k0_matches_reference_golden(eng):
+    g = load_golden("primitives.json.gz")[0]
+    recs = [r for r in scenario_reads("h1")[:280]]
+    keep = []
+    for a, s, q in recs:
+        seqc, _ = oc.hpol_compress(s)
+        if len(seqc) >= 13 and len(s) >= 26:
+            keep.append((s, q))
+    eng.upload_records(keep)
+    eng.quality_stats()
+    ec, eu, _bk = eng.get_quality_stats()
+    assert [repr(float(x)) for x in ec] == [r["err_c"] for r in g["reads"]]
+    assert [repr(float(x)) for x in eu] == [r["err_u"] for r in g["reads"]]
+
+
+def _oracle_align(lib, a, b, o, k, m):
+    nc, sc = ctypes.c_int(0), ctypes.c_int(0)
+    c = lib.oracle_sg_block_align(a.encode(), len(a), b.encode(), len(b), o, 1, k, m, ctypes.byref(nc), ctypes.byref(sc))
+    return c, sc.value
+
+
+def test_k4_block_align_random_pairs(eng):
+    lib = oc._lib()
+    rng = np.random.default_rng(11)
+
+    def rnd(n):
+        return "".join(rng.choice(list("ACGT"), size=n))
+
+    def mutate(s, e):
+        out = []
+        for ch in s:
+            r = rng.random()
+            if r < e / 3:
+                continue
+            if r < 2 * e / 3:
+                out.append("ACGT"[rng.integers(4)])
+            if r < e:
+                out.append("ACGT"[rng.integers(4)])
+                continue
+            out.append(ch)
+        return "".join(out) or "A"
+
+    reads, pairs = [], []
+    for L in [1, 2, 5, 12, 13, 14, 30, 100, 255, 256, 257, 300, 511, 513, 750, 800, 1100, 2000]:
+        for e in (0.0, 0.05, 0.15, 0.3):
+            a = rnd(L)
+            b = mutate(a, e)
+            reads += [a, b]
+            pairs.append((len(reads) - 2, len(reads) - 1))
+        a, b = rnd(L), rnd(max(1, L // 2 + 3))
+        reads += [a, b]
+        pairs.append((len(reads) - 2, len(reads) - 1))
+        pairs.append((len(reads) - 1, len(reads) - 2))
+        # overlap (dovetail) and containment
+        a = rnd(L + 40)
+        reads += [a[: L + 10], a[20:]]
+        pairs.append((len(reads) - 2, len(reads) - 1))
+    eng.upload_records([(s, "5" * len(s)) for s in reads])
+    for k in (13, 15, 5):
+        A, B, O, M = [], [], [], []
+        for (x, y) in pairs:
+            for o in (2, 3, 5):
+                for m in (1, 7, k - 2, k):
+                    A.append(x); B.append(y); O.append(o); M.append(m)
+        cnt, score = eng.sg_block_align(A, B, O, M, k, want_score=True)
+        for i in range(len(A)):
+            ec, es = _oracle_align(lib, reads[A[i]], reads[B[i]], O[i], k, M[i])
+            assert (int(cnt[i]), int(score[i])) == (ec, es), (len(reads[A[i]]), len(reads[B[i]]), O[i], k, M[i])
+
+
+def _run_scenario(tag, p_table):
+    from ngspeciesid_b200.modules import parallelize
+    g = load_golden("clusters_%s.json.gz" % tag)
+    args = scenario_args(g)
+    args.device = 0
+    srt = oc.sort_stage(scenario_reads(tag), args.k)
+    ra = oc.read_array_from_sorted(srt)
+    p_emp = oc.load_p_emp(p_table, args.k, args.w)
+    if args.nr_cores > 1:
+        clusters, reps = parallelize.parallel_clustering(ra, p_emp, args)
+    else:
+        clusters, reps = parallelize.single_clustering(ra, p_emp, args)
+    idx_of = {r[2]: r[0] for r in ra}
+    out = oc.output_order(clusters, reps)
+    got = [[idx_of[a] for a in accs] for _rep, accs in out]
+    assert got == g["clusters"]
+    origins = [[i, rep, repr(reps[rep][5]), repr(reps[rep][6])] for i, (rep, _a) in enumerate(out)]
+    assert origins == [o[:4] for o in g["origins"]]
+    for rep, _a in out:
+        assert reps[rep][7] == oc.hpol_compress(reps[rep][3])[0]
+
+
+@pytest.mark.parametrize("tag", ["h1_t1", "h1_t4", "h1_sym_t1", "supp1k_t1", "supp1k_t8",
+                                 "synth2k_t1", "synth2k_t8", "synthpb_t1"])
+def test_clustering_matches_reference_golden(tag, p_table):
+    _run_scenario(tag, p_table)
+
+
+def _mixed_reads(n, seed):
+    """Species reads plus a large share of unrelated junk reads, so that new representatives,
+    chains of tentative representatives and re-evaluations all occur."""
+    from ngspeciesid_b200.synth import simulate_reads
+    rng = np.random.default_rng(seed)
+    rs = simulate_reads(n, n_species=6, len_lo=300, len_hi=400, seed=seed)
+    recs = list(rs.records())
+    junk = []
+    for i in range(n // 3):
+        L = int(rng.integers(200, 420))
+        s = "".join(rng.choice(list("ACGT"), size=L))
+        q = "".join(chr(33 + int(x)) for x in rng.integers(8, 30, size=L))
+        junk.append(("junk%d" % i, s, q))
+    allr = recs + junk
+    perm = rng.permutation(len(allr))
+    return [allr[i] for i in perm]
+
+
+@pytest.mark.parametrize("seed,tile", [(21, 0), (22, 64), (23, 1000)])
+def test_clustering_matches_oracle_with_many_representatives(eng, p_table, seed, tile):
+    from ngspeciesid_b200 import engine as E
+    recs = _mixed_reads(900, seed)
+    srt = oc.sort_stage(recs, 13)
+    ra = oc.read_array_from_sorted(srt)
+    args = oc.default_args()
+    p_emp = oc.load_p_emp(p_table, 13, 20)
+    stats = oc.Stats()
+    oc.single_clustering(ra, p_emp, args, stats)
+    exp = [(-1 if w < 0 else w) for _rid, w, _how in stats.trace]
+    eng.upload_records([(r[3], r[4]) for r in ra])
+    eng.minimizers(13, 20)
+    eng.quality_stats()
+    assign, via, st = eng.cluster(13, 20, E.max_gap_table(p_emp, 0.1), np.arange(len(ra)),
+                                  E.accession_ranks([r[2] for r in ra]), tile_reads=tile)
+    assert list(assign) == exp
+    how = {"new": 0, "map": 1, "align": 2}
+    assert list(via) == [how[h] for _r, _w, h in stats.trace]
+    assert st["n_new_reps"] == sum(1 for x in exp if x < 0) > 100
