@@ -41,6 +41,11 @@ int ngsid_version(void);                               /* ABI version, currently
 int64_t ngsid_launch_count(const ngsid_ctx *ctx);
 void ngsid_reset_launch_count(ngsid_ctx *ctx);
 int ngsid_sync(ngsid_ctx *ctx);
+/* Device time (CUDA events on the context's stream) of the most recent run of a phase, in ms:
+ * which = 0 pack (inside upload), 1 K1 minimizers, 2 K0 quality stats, 3 whole clustering pass,
+ * 4 sum of K4 launches inside the last clustering pass, 5 sum of map launches inside it.
+ * Returns a negative value when that phase has not run.                                        */
+float ngsid_phase_ms(ngsid_ctx *ctx, int which);
 
 /* ---- read upload ---------------------------------------------------------------------------
  * seq / qual: ASCII bases and PHRED+33 qualities of n_reads reads, concatenated; offsets has

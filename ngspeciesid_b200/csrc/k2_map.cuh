@@ -344,6 +344,7 @@ __global__ void k2_apply_align_kernel(const AlignRequest *__restrict__ req, int 
     AlignRequest rq = req[i];
     double n1 = (double)(off[rq.read_a + 1] - off[rq.read_a]);
     double n2 = (double)(off[rq.read_b + 1] - off[rq.read_b]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(err_flag + 2), (unsigned long long)(n1 * n2));
     double ratio = __ddiv_rn((double)k4cnt[i], n1);
     if (params->symmetric) ratio = fmin(ratio, __ddiv_rn((double)k4cnt[i], n2));
     int passed = ratio >= params->aligned_threshold ? 1 : 0;

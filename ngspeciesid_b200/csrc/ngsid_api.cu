@@ -29,8 +29,22 @@ extern "C" int ngsid_ctx_create(int device_id, ngsid_ctx **out)
         delete ctx;
         return NGSID_ECUDA;
     }
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (cudaEventCreate(&ctx->pev[i][j]) != cudaSuccess) { delete ctx; return NGSID_ECUDA; }
     *out = ctx;
     return NGSID_OK;
+}
+
+extern "C" float ngsid_phase_ms(ngsid_ctx *ctx, int which)
+{
+    if (!ctx || which < 0 || which > 5) return -1.f;
+    if (which >= 4) return ctx->pev_valid[which] ? ctx->phase_acc[which] : -1.f;
+    if (!ctx->pev_valid[which]) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(ctx->pev[which][1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, ctx->pev[which][0], ctx->pev[which][1]) != cudaSuccess) return -1.f;
+    return ms;
 }
 
 extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
@@ -46,6 +60,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
                       &ctx->d_newslots, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
     for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -103,9 +118,12 @@ extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, 64, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_packed.p, 0, (size_t)wsum * 4 + 64, ctx->stream));
     int blocks = (int)std::min<int64_t>((n_reads + 7) / 8, (int64_t)ctx->sm_count * 16);
+    cudaEventRecord(ctx->pev[0][0], ctx->stream);
     k_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_off.as<int64_t>(),
                                                    ctx->d_woff.as<int64_t>(), ctx->d_packed.as<uint32_t>(),
                                                    n_reads, ctx->d_flag.as<int>());
+    cudaEventRecord(ctx->pev[0][1], ctx->stream);
+    ctx->pev_valid[0] = true;
     KERNEL_CHECK(ctx);
     int flag = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -176,7 +194,10 @@ extern "C" int ngsid_minimizers(ngsid_ctx *ctx, int k, int w)
     int rc = k1_prepare(ctx, k, w);
     if (rc) return rc;
     if (ctx->n_reads == 0) { ctx->have_min = true; return NGSID_OK; }
+    cudaEventRecord(ctx->pev[1][0], ctx->stream);
     rc = k1_launch(ctx);
+    cudaEventRecord(ctx->pev[1][1], ctx->stream);
+    ctx->pev_valid[1] = true;
     if (rc) return rc;
     ctx->have_min = true;
     ctx->h_nmin_valid = false;
@@ -268,10 +289,13 @@ extern "C" int ngsid_quality_stats(ngsid_ctx *ctx, const double *phred_p, const 
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_thr.p, bucket_thresholds, 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if (n) {
         int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
+        cudaEventRecord(ctx->pev[2][0], ctx->stream);
         k0_quality_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_qual.as<uint8_t>(),
                                                            ctx->d_off.as<int64_t>(), ctx->d_phred.as<double>(),
                                                            ctx->d_thr.as<double>(), ctx->d_errc.as<double>(),
                                                            ctx->d_erru.as<double>(), ctx->d_bucket.as<uint8_t>(), n);
+        cudaEventRecord(ctx->pev[2][1], ctx->stream);
+        ctx->pev_valid[2] = true;
         KERNEL_CHECK(ctx);
     }
     ctx->have_q = true;
@@ -353,6 +377,36 @@ extern "C" int ngsid_sg_block_align(ngsid_ctx *ctx, const int32_t *read_a, const
 
 // ================================================================================ clustering driver
 namespace {
+
+// pair of events around a launch; resolved (summed per kind) at the end of the pass
+static void ev_begin(ngsid_ctx *ctx, int kind)
+{
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        ctx->ev_pool.push_back(a); ctx->ev_pool.push_back(b);
+    }
+    if (ctx->ev_kind.size() < ctx->ev_pool.size() / 2) ctx->ev_kind.resize(ctx->ev_pool.size() / 2);
+    ctx->ev_kind[ctx->ev_used / 2] = kind;
+    cudaEventRecord(ctx->ev_pool[ctx->ev_used], ctx->stream);
+}
+static void ev_end(ngsid_ctx *ctx)
+{
+    if (ctx->ev_used + 2 > ctx->ev_pool.size()) return;
+    cudaEventRecord(ctx->ev_pool[ctx->ev_used + 1], ctx->stream);
+    ctx->ev_used += 2;
+}
+static void ev_resolve(ngsid_ctx *ctx)
+{
+    ctx->phase_acc[4] = ctx->phase_acc[5] = 0.f;
+    for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i], ctx->ev_pool[i + 1]) == cudaSuccess)
+            ctx->phase_acc[ctx->ev_kind[i / 2]] += ms;
+    }
+    ctx->pev_valid[4] = ctx->pev_valid[5] = true;
+    ctx->ev_used = 0;
+}
 
 struct ClusterRun {
     ngsid_ctx *ctx;
@@ -471,7 +525,9 @@ int ClusterRun::run_map(const int32_t *d_list, int n_list)
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_reqn.p, 0, 4, ctx->stream));
         A.list = list; A.n_list = nl;
         int blocks = std::min(map_blocks, (nl + 7) / 8);
+        ev_begin(ctx, 5);
         k2_map_kernel<<<blocks, 256, 0, ctx->stream>>>(A);
+        ev_end(ctx);
         KERNEL_CHECK(ctx);
         st.n_map_launch_reads += nl;
         int32_t hdr[2] = {0, 0};
@@ -482,8 +538,10 @@ int ClusterRun::run_map(const int32_t *d_list, int n_list)
         int nreq = hdr[0];
         if (nreq == 0) return NGSID_OK;
         const AlignRequest *rq = ctx->d_req.as<AlignRequest>();
+        ev_begin(ctx, 4);
         int rc = k4_launch(ctx, &rq->read_a, &rq->read_b, &rq->open, &rq->match_id, 6, nreq, ctx->k,
                            ctx->d_k4cnt.as<int32_t>(), nullptr);
+        ev_end(ctx);
         if (rc) return rc;
         st.n_alignments += nreq;
         k2_apply_align_kernel<<<(nreq + 255) / 256, 256, 0, ctx->stream>>>(rq, nreq, ctx->d_k4cnt.as<int32_t>(),
@@ -524,6 +582,9 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     int rc = fetch_nmin(ctx);
     if (rc) return rc;
 
+    cudaEventRecord(ctx->pev[3][0], ctx->stream);
+    ctx->pev_valid[3] = false;
+    ctx->ev_used = 0;
     ClusterRun R;
     R.ctx = ctx;
     R.n = n_order;
@@ -697,12 +758,18 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
         T = std::max(32, T / 2);
     }
 
+    cudaEventRecord(ctx->pev[3][1], ctx->stream);
+    ctx->pev_valid[3] = true;
     // ---- results
     std::vector<uint8_t> h_via(n);
+    unsigned long long cells = 0;
     if (n) {
         CUDA_TRY(ctx, cudaMemcpyAsync(h_via.data(), ctx->d_via.p, n, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaMemcpyAsync(&cells, R.d_err.as<uint8_t>() + 8, 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ev_resolve(ctx);
+    R.st.align_cells = (int64_t)cells;
     for (int i = 0; i < n; ++i) {
         int d = R.h_dec[i];
         out_assign[i] = d;

@@ -37,6 +37,12 @@ struct ngsid_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t pev[6][2] = {};
+    bool pev_valid[6] = {false, false, false, false, false, false};
+    float phase_acc[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<cudaEvent_t> ev_pool;     // pairs of events around launches inside a clustering pass
+    std::vector<int> ev_kind;
+    size_t ev_used = 0;
     std::string err;
     int64_t launches = 0;
 

@@ -117,8 +117,9 @@ def simulate_reads(n_reads, n_species=10, len_lo=700, len_hi=800, seed=1002, pro
                    independent=False, templates=None, per_read_len=None):
     """Returns a ReadSet of n_reads synthetic amplicon reads.
 
-    per_read_len: optional (lo, hi); when given every read is a random-length prefix window of its
+    per_read_len: optional (lo, hi); when given every read covers a random-length prefix of its
     template (used by the mixed-length PacBio configuration, templates then being >= hi long).
+    Vectorised over all reads that share a (species, strand) template.
     """
     rng = np.random.default_rng(seed)
     if templates is None:
@@ -128,63 +129,77 @@ def simulate_reads(n_reads, n_species=10, len_lo=700, len_hi=800, seed=1002, pro
     species = rng.integers(0, n_species, size=n_reads)
     strand = rng.integers(0, 2, size=n_reads).astype(np.uint8)
     erate = np.clip(rng.normal(mean, sd, size=n_reads), lo, hi)
+    p_del, p_ins, _p_sub = split
 
-    fw = [t for t in templates]
-    rc = [_COMP[t[::-1]] for t in templates]
-    # homopolymer membership weight per template position
     def hp_weight(t):
         same_prev = np.zeros(len(t), dtype=bool)
         same_prev[1:] = t[1:] == t[:-1]
         same_next = np.zeros(len(t), dtype=bool)
         same_next[:-1] = t[1:] == t[:-1]
         return np.where(same_prev | same_next, hw, 1.0)
-    fw_w = [hp_weight(t) for t in fw]
-    rc_w = [hp_weight(t) for t in rc]
 
-    seq_parts, qual_parts = [], []
+    lengths = np.zeros(n_reads, dtype=np.int64)
+    chunks = {}                         # read index -> (bases, quals) views, filled per group
+    group_out = []
+    for s in range(n_species):
+        for st in (0, 1):
+            idx = np.nonzero((species == s) & (strand == st))[0]
+            if len(idx) == 0:
+                continue
+            t = templates[s] if st == 0 else _COMP[templates[s][::-1]]
+            w = hp_weight(t)
+            L = len(t)
+            n = len(idx)
+            e = erate[idx][:, None]
+            if per_read_len is not None:
+                ln = rng.integers(per_read_len[0], min(per_read_len[1], L) + 1, size=n)
+                live = np.arange(L)[None, :] < ln[:, None]
+                wsum = np.where(live, w[None, :], 0.0).sum(axis=1)[:, None]
+                lnf = ln[:, None].astype(np.float64)
+            else:
+                live = None
+                wsum = w.sum()
+                lnf = float(L)
+            pe = np.minimum(e * w[None, :] * (lnf / wsum), 0.9)
+            err = rng.random((n, L)) < pe
+            kind = rng.random((n, L))
+            is_del = err & (kind < p_del)
+            is_ins = err & (kind >= p_del) & (kind < p_del + p_ins)
+            is_sub = err & (kind >= p_del + p_ins)
+            code = np.broadcast_to(np.searchsorted(_ACGT, t)[None, :], (n, L))
+            shift = rng.integers(1, 4, size=(n, L))
+            bases = _ACGT[np.where(is_sub, (code + shift) & 3, code)]
+            qmean = -10.0 * np.log10(e)
+            q = np.clip(np.rint(rng.normal(qmean, 4.0, size=(n, L))), 2, 50)
+            low = is_sub | is_ins
+            q = np.where(low, np.minimum(q, rng.integers(2, 9, size=(n, L))), q)
+            reps = np.ones((n, L), dtype=np.int64)
+            reps[is_del] = 0
+            reps[is_ins] = 2
+            if live is not None:
+                reps[~live] = 0
+            flat_reps = reps.ravel()
+            out_b = np.repeat(bases.ravel(), flat_reps)
+            out_q = np.repeat(q.ravel(), flat_reps)
+            ins_flat = (is_ins if live is None else (is_ins & live)).ravel()
+            nins = int(ins_flat.sum())
+            if nins:
+                pos = np.cumsum(flat_reps)[ins_flat] - 1
+                out_b[pos] = _ACGT[rng.integers(0, 4, size=nins)]
+                out_q[pos] = rng.integers(2, 9, size=nins)
+            lens = reps.sum(axis=1)
+            lengths[idx] = lens
+            group_out.append((idx, lens, out_b, (out_q + 33).astype(np.uint8)))
     offsets = np.zeros(n_reads + 1, dtype=np.int64)
-    p_del, p_ins, p_sub = split
-    for i in range(n_reads):
-        s = species[i]
-        t, w = (fw[s], fw_w[s]) if strand[i] == 0 else (rc[s], rc_w[s])
-        if per_read_len is not None:
-            ln = int(rng.integers(per_read_len[0], min(per_read_len[1], len(t)) + 1))
-            t, w = t[:ln], w[:ln]
-        L = len(t)
-        e = erate[i]
-        # normalise so that the expected error fraction stays e
-        pe = np.minimum(e * w * (L / w.sum()), 0.9)
-        u = rng.random(L)
-        err = u < pe
-        kind = rng.random(L)
-        is_del = err & (kind < p_del)
-        is_ins = err & (kind >= p_del) & (kind < p_del + p_ins)
-        is_sub = err & (kind >= p_del + p_ins)
-        bases = t.copy()
-        nsub = int(is_sub.sum())
-        if nsub:
-            shift = rng.integers(1, 4, size=nsub)
-            code = np.searchsorted(_ACGT, bases[is_sub])  # A,C,G,T are sorted ASCII
-            bases[is_sub] = _ACGT[(code + shift) & 3]
-        # qualities
-        qmean = -10.0 * np.log10(e)
-        q = np.clip(np.rint(rng.normal(qmean, 4.0, size=L)), 2, 50)
-        low = is_sub | is_ins
-        q[low] = np.minimum(q[low], rng.integers(2, 9, size=int(low.sum())))
-        reps = np.ones(L, dtype=np.int64)
-        reps[is_del] = 0
-        reps[is_ins] = 2
-        out_b = np.repeat(bases, reps)
-        out_q = np.repeat(q, reps)
-        nins = int(is_ins.sum())
-        if nins:
-            # second copy of each inserted position becomes a random base with low quality
-            pos = np.cumsum(reps)[is_ins] - 1
-            out_b[pos] = _ACGT[rng.integers(0, 4, size=nins)]
-            out_q[pos] = rng.integers(2, 9, size=nins)
-        seq_parts.append(out_b)
-        qual_parts.append((out_q + 33).astype(np.uint8))
-        offsets[i + 1] = offsets[i] + len(out_b)
-    seq = np.concatenate(seq_parts) if seq_parts else np.zeros(0, np.uint8)
-    qual = np.concatenate(qual_parts) if qual_parts else np.zeros(0, np.uint8)
+    np.cumsum(lengths, out=offsets[1:])
+    seq = np.empty(offsets[-1], dtype=np.uint8)
+    qual = np.empty(offsets[-1], dtype=np.uint8)
+    for idx, lens, out_b, out_q in group_out:
+        # destination index of every base of the group = start of its read + rank inside the read
+        starts = offsets[idx]
+        gofs = np.zeros(len(idx) + 1, dtype=np.int64)
+        np.cumsum(lens, out=gofs[1:])
+        dest = np.repeat(starts - gofs[:-1], lens) + np.arange(gofs[-1])
+        seq[dest] = out_b
+        qual[dest] = out_q
     return ReadSet(seq, qual, offsets, species=species, strand=strand, templates=templates)
