@@ -46,6 +46,9 @@ int ngsid_sync(ngsid_ctx *ctx);
  * 4 sum of K4 launches inside the last clustering pass, 5 sum of map launches inside it.
  * Returns a negative value when that phase has not run.                                        */
 float ngsid_phase_ms(ngsid_ctx *ctx, int which);
+/* Tuning / test switches. option 1: value != 0 forces the generic warp-per-read K1 kernel for
+ * every (k, w) (the thread-per-read fast kernel otherwise serves w-k+1 == 8, k <= 13).         */
+int ngsid_set_option(ngsid_ctx *ctx, int option, int value);
 
 /* ---- read upload ---------------------------------------------------------------------------
  * seq / qual: ASCII bases and PHRED+33 qualities of n_reads reads, concatenated; offsets has

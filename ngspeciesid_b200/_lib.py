@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsid.so")
 
 EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last_error",
-           "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_upload_reads",
+           "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
            "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_cluster", "ngsid_sg_block_align"]
 
@@ -59,6 +59,7 @@ def load():
     lib.ngsid_sync.argtypes = [vp]
     lib.ngsid_phase_ms.argtypes = [vp, i32]
     lib.ngsid_phase_ms.restype = ctypes.c_float
+    lib.ngsid_set_option.argtypes = [vp, i32, i32]
     lib.ngsid_upload_reads.argtypes = [vp, vp, vp, vp, i64]
     lib.ngsid_minimizers.argtypes = [vp, i32, i32]
     lib.ngsid_minimizers_timed.argtypes = [vp, i32, i32, i32, P(ctypes.c_float)]

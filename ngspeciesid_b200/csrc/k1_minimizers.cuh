@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256)
 k1_minimizers_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ woff,
                      const int64_t *__restrict__ off, const int64_t *__restrict__ moff,
                      Minimizer *__restrict__ mins, uint32_t *__restrict__ nmin,
-                     uint32_t *__restrict__ lenc, int64_t n_reads, int k, int w, int lcap)
+                     uint32_t *__restrict__ lenc, int64_t n_reads, int k, int w, int lcap,
+                     const int32_t *__restrict__ list, const int32_t *__restrict__ list_n)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warps_per_block = blockDim.x >> 5;
@@ -70,8 +71,11 @@ k1_minimizers_kernel(const uint32_t *__restrict__ packed, const int64_t *__restr
     uint8_t *cs = reinterpret_cast<uint8_t *>(cp + (lcap / 16 + 4));
     const int W = w - k + 1;
 
-    for (int64_t r = (int64_t)blockIdx.x * warps_per_block + wid; r < n_reads;
-         r += (int64_t)gridDim.x * warps_per_block) {
+    // optional work list (reads the fast kernel handed over): entries [0, *list_n)
+    const int64_t n_work = list ? (int64_t)*list_n : n_reads;
+    for (int64_t wi_ = (int64_t)blockIdx.x * warps_per_block + wid; wi_ < n_work;
+         wi_ += (int64_t)gridDim.x * warps_per_block) {
+        const int64_t r = list ? (int64_t)list[wi_] : wi_;
         const int L = (int)(off[r + 1] - off[r]);
         const uint32_t *pk = packed + woff[r];
         Minimizer *out = mins + moff[r];
@@ -169,6 +173,150 @@ k1_minimizers_kernel(const uint32_t *__restrict__ packed, const int64_t *__restr
         }
         __syncwarp();
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// K1 fast path (w - k + 1 == 8, k <= 13): one THREAD per read, all state in registers.
+//   * 4 bases at a time go through a 1024-entry shared-memory table (previous base, packed byte)
+//     -> (kept bases, count): homopolymer compression without a per-base branch;
+//   * kept bases queue up in a 64-bit FIFO; every 8 of them form a block: rolling 2k-bit code per
+//     slot, key = code << 4 | slot-in-block, and the sliding minimum over 8 k-mers is
+//     min(suffix minimum of the previous block, prefix minimum of this block) (van Herk /
+//     Gil-Werman), branch-free, leftmost on ties because the slot index sits in the low key bits;
+//   * a minimizer is written whenever the argmin slot of consecutive windows changes.
+// Reads whose compressed length is < w (reference quirk, one truncated-window minimizer) are
+// appended to `slow_list` and finished by k1_minimizers_kernel.
+#define K1F_INF 0xffffffffu
+
+struct K1FastState {
+    uint32_t suf[9];
+    uint32_t code;
+    int base;          // slot index of the first slot of the next block
+    int last_slot;
+    uint32_t n_out;
+};
+
+template <bool PARTIAL>
+__device__ __forceinline__ void k1_fast_block(K1FastState &S, uint32_t ch, int nvalid, int k, int w,
+                                              uint32_t kmask, Minimizer *__restrict__ out)
+{
+    uint32_t key[8];
+    uint32_t pm = K1F_INF;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        uint32_t b = (ch >> (14 - 2 * t)) & 3u;
+        S.code = ((S.code << 2) | b) & kmask;
+        const int slot = S.base + t;
+        uint32_t kk = (S.code << 4) | (uint32_t)(8 + t);
+        if (slot < k - 1) kk = K1F_INF;
+        if (PARTIAL && t >= nvalid) kk = K1F_INF;
+        key[t] = kk;
+        pm = min(pm, kk);
+        const uint32_t m = min(S.suf[t + 1], pm);
+        const int mslot = S.base - 8 + (int)(m & 15u);
+        bool emit = (slot >= w - 1) && (mslot != S.last_slot);
+        if (PARTIAL) emit = emit && (t < nvalid);
+        if (emit) {
+            out[S.n_out] = make_uint2(m >> 4, (uint32_t)(mslot - (k - 1)));
+            S.n_out++;
+            S.last_slot = mslot;
+        }
+    }
+    uint32_t sm = K1F_INF;
+#pragma unroll
+    for (int t = 7; t >= 0; --t) {
+        sm = min(sm, key[t]);
+        S.suf[t] = sm - 8u;          // becomes "previous block": slot tags 0..7
+    }
+    S.base += 8;
+}
+
+__global__ void __launch_bounds__(128)
+k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ woff,
+               const int64_t *__restrict__ off, const int64_t *__restrict__ moff,
+               Minimizer *__restrict__ mins, uint32_t *__restrict__ nmin,
+               uint32_t *__restrict__ lenc, int64_t n_reads, int k, int w,
+               int32_t *__restrict__ slow_list, int32_t *__restrict__ slow_n)
+{
+    __shared__ uint16_t lut[1024];
+    for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) {
+        uint32_t prev = idx >> 8, byte = idx & 255, bits = 0, cnt = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            uint32_t b = (byte >> (6 - 2 * t)) & 3u;
+            if (b != prev) { bits = (bits << 2) | b; cnt++; }
+            prev = b;
+        }
+        lut[idx] = (uint16_t)((cnt << 8) | bits);
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const int L = (int)(off[r + 1] - off[r]);
+    const uint4 *pk = reinterpret_cast<const uint4 *>(packed + woff[r]);
+    Minimizer *out = mins + moff[r];
+    const uint32_t kmask = (1u << (2 * k)) - 1u;
+
+    K1FastState S;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) S.suf[t] = K1F_INF;
+    S.code = 0; S.base = 0; S.last_slot = -1; S.n_out = 0;
+    unsigned long long fifo = 0;
+    int avail = 0;
+    uint32_t prev = 0;
+    const int nwords_full = L >> 4;
+    const int nquads = (L + 63) >> 6;
+    uint4 cur = (nquads > 0) ? __ldg(pk) : make_uint4(0, 0, 0, 0);
+    if (L > 0) prev = (cur.x >> 30) ^ 1u;             // anything different from the first base
+    for (int qd = 0; qd < nquads; ++qd) {
+        uint4 nxt = (qd + 1 < nquads) ? __ldg(pk + qd + 1) : make_uint4(0, 0, 0, 0);
+        uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) {
+            const int wi = qd * 4 + wq;
+            uint32_t word = words[wq];
+            if (wi < nwords_full) {
+#pragma unroll
+                for (int bq = 0; bq < 4; ++bq) {
+                    uint32_t byte = word >> 24;
+                    word <<= 8;
+                    uint32_t e = lut[(prev << 8) | byte];
+                    uint32_t c = e >> 8;
+                    fifo = (fifo << (2 * c)) | (unsigned long long)(e & 255u);
+                    avail += (int)c;
+                    prev = byte & 3u;
+                }
+            } else if (wi == nwords_full) {
+                const int rem = L & 15;
+                for (int t = 0; t < rem; ++t) {
+                    uint32_t b = word >> 30;
+                    word <<= 2;
+                    if (b != prev) { fifo = (fifo << 2) | b; avail++; }
+                    prev = b;
+                }
+            }
+            while (avail >= 8) {
+                uint32_t ch = (uint32_t)(fifo >> (2 * (avail - 8))) & 0xffffu;
+                avail -= 8;
+                k1_fast_block<false>(S, ch, 8, k, w, kmask, out);
+            }
+        }
+        cur = nxt;
+    }
+    const int Lc = S.base + avail;
+    if (avail > 0) {
+        uint32_t ch = (uint32_t)(fifo << (2 * (8 - avail))) & 0xffffu;
+        k1_fast_block<true>(S, ch, avail, k, w, kmask, out);
+    }
+    if (Lc < w) {
+        // compressed read shorter than w (or than k): the generic kernel reproduces the quirk
+        int i = atomicAdd(slow_n, 1);
+        slow_list[i] = (int32_t)r;
+        return;
+    }
+    nmin[r] = S.n_out;
+    lenc[r] = (uint32_t)Lc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -47,6 +47,13 @@ extern "C" float ngsid_phase_ms(ngsid_ctx *ctx, int which)
     return ms;
 }
 
+extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
+{
+    if (!ctx) return NGSID_EINVAL;
+    if (option == 1) { ctx->force_generic_k1 = value != 0; ctx->have_min = false; return NGSID_OK; }
+    return fail(ctx, NGSID_EINVAL, "unknown option");
+}
+
 extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
 {
     if (!ctx) return;
@@ -96,7 +103,7 @@ extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint
         int64_t L = offsets[i + 1] - offsets[i];
         if (L < 0 || L > (1 << 24)) return fail(ctx, NGSID_EINVAL, "bad read length");
         ctx->h_woff[i] = wsum;
-        wsum += (L + 15) / 16 + 1;                   // one spare word per read
+        wsum += (((L + 15) / 16 + 1) + 3) / 4 * 4;   // >= one spare word; reads start 16-B aligned
         maxlen = std::max<int>(maxlen, (int)L);
     }
     ctx->h_woff[n_reads] = wsum;
@@ -161,15 +168,11 @@ static int k1_prepare(ngsid_ctx *ctx, int k, int w)
     return NGSID_OK;
 }
 
-static int k1_launch(ngsid_ctx *ctx)
+static int k1_launch_generic(ngsid_ctx *ctx, const int32_t *list, const int32_t *list_n, int64_t n_work)
 {
     int lcap = ((ctx->max_len + 31) / 32) * 32 + 32;
-    size_t per_warp = k1_smem_per_warp(lcap);
-    per_warp = (per_warp + 15) / 16 * 16;
-    // keep lcap-derived stride 16-aligned: per-warp size is computed inside the kernel from lcap
-    if (k1_smem_per_warp(lcap) % 16 != 0) lcap += 16 - (int)((k1_smem_per_warp(lcap) % 16));
     while (k1_smem_per_warp(lcap) % 16 != 0) lcap += 4;
-    per_warp = k1_smem_per_warp(lcap);
+    size_t per_warp = k1_smem_per_warp(lcap);
     int wpb = (int)std::min<size_t>(8, SMEM_BUDGET / per_warp);
     if (wpb < 1) return fail(ctx, NGSID_EUNSUPPORTED, "read too long for the K1 shared-memory tile");
     size_t smem = per_warp * wpb;
@@ -177,14 +180,32 @@ static int k1_launch(ngsid_ctx *ctx)
     int bps = 1;
     CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k1_minimizers_kernel, wpb * 32, smem));
     bps = std::max(1, bps);
-    int64_t need = (ctx->n_reads + wpb - 1) / wpb;
+    int64_t need = (n_work + wpb - 1) / wpb;
     int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * bps));
     k1_minimizers_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(
         ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
         ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
-        ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, lcap);
+        ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, lcap, list, list_n);
     KERNEL_CHECK(ctx);
     return NGSID_OK;
+}
+
+static int k1_launch(ngsid_ctx *ctx)
+{
+    const bool fast = (ctx->w - ctx->k + 1 == 8) && ctx->k <= 13 && !ctx->force_generic_k1;
+    if (!fast) return k1_launch_generic(ctx, nullptr, nullptr, ctx->n_reads);
+    // fast path + hand-over list for reads with compressed length < w
+    CUDA_TRY(ctx, ctx->d_newslots.ensure((size_t)(ctx->n_reads + 16) * 4));
+    int32_t *slow_n = ctx->d_newslots.as<int32_t>();
+    int32_t *slow_list = slow_n + 4;
+    CUDA_TRY(ctx, cudaMemsetAsync(slow_n, 0, 16, ctx->stream));
+    int blocks = (int)((ctx->n_reads + 127) / 128);
+    k1_fast_kernel<<<blocks, 128, 0, ctx->stream>>>(
+        ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
+        ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
+        ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, slow_list, slow_n);
+    KERNEL_CHECK(ctx);
+    return k1_launch_generic(ctx, slow_list, slow_n, std::min<int64_t>(ctx->n_reads, 4096));
 }
 
 extern "C" int ngsid_minimizers(ngsid_ctx *ctx, int k, int w)

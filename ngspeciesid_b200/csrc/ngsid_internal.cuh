@@ -56,6 +56,7 @@ struct ngsid_ctx {
     // ---- K1 results
     int k = 0, w = 0;
     bool have_min = false;
+    bool force_generic_k1 = false;    // tests: run the warp-per-read kernel for every (k,w)
     std::vector<int64_t> h_moff;      // n+1 offsets into d_mins (slack CSR: capacity per read)
     std::vector<uint32_t> h_nmin;     // mirror of d_nmin (filled lazily)
     bool h_nmin_valid = false;

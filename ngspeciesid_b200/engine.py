@@ -190,6 +190,9 @@ class Engine(object):
         self._check(self.lib.ngsid_sg_block_align(self.h, ptr(a), ptr(b), ptr(o), ptr(m), len(a), k, ptr(cnt), ptr(score)))
         return (cnt, score) if want_score else cnt
 
+    def set_option(self, option, value):
+        self._check(self.lib.ngsid_set_option(self.h, option, value))
+
     def phase_ms(self, which):
         return float(self.lib.ngsid_phase_ms(self.h, which))
 

@@ -1,0 +1,318 @@
+/*
+ * oracle/poa_oracle.cpp -- TEST INFRASTRUCTURE ONLY (never imported by the product path).
+ *
+ * CPU restatement of the partial-order-alignment consensus the reference obtains by shelling out
+ * to the third-party binaries spoa (4.0.7, Dockerfile:14) and racon (1.4.20, Dockerfile:15), none
+ * of which is vendored under /root/reference or installable here.
+ *
+ * Reference call sites:
+ *   modules/consensus.py:83-92    run_spoa:  `spoa <fastq> -l 0 -r 0 -g -2`  -> line 2 of stdout
+ *   modules/consensus.py:107-126  run_racon: racon_iter x (minimap2 -x map-ont ; racon) (see
+ *                                 oracle/consensus_oracle.py for the windowing restatement)
+ *
+ * PARITY UNPINNED: no spoa/racon output exists anywhere in the reference (it has no tests), so
+ * this file follows spoa's published algorithm (Lee 2002 POA; Vaser 2017 racon/spoa):
+ *   - graph of nodes (one letter each), weighted directed edges, groups of mutually "aligned"
+ *     nodes (alternative letters of one column);
+ *   - a sequence is aligned to the graph by DP over the topologically ordered nodes
+ *     (rows) x sequence positions (columns); spoa's engine picks LINEAR gaps when g >= e, so
+ *     `-g -2` (e defaults to -6) means gap = -2 per base; `-l 0` = local (Smith-Waterman),
+ *     m = +5, n = -4; racon's windows use global alignment with m = 3, n = -5, g = -4;
+ *   - FASTQ qualities are per-base weights (q - 33); an edge accumulates the sum of the two
+ *     base weights of every sequence that traverses it;
+ *   - consensus = heaviest bundle: per node the heaviest in-edge (ties -> predecessor with the
+ *     higher score), best-scoring node, completed forward to a sink, then backtracked.
+ * Traceback preference: diagonal through the predecessors in edge-insertion order, then
+ * "graph node against a gap", then "sequence base against a gap".
+ */
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+struct Edge { int from, to; long long w; };
+
+struct Graph {
+    std::vector<char> letter;
+    std::vector<std::vector<int>> in, out;      // edge ids, insertion order
+    std::vector<std::vector<int>> aligned;      // node ids
+    std::vector<Edge> edges;
+    std::vector<int> order;                     // topological order (rank -> node)
+    std::vector<int> rank;                      // node -> rank
+    std::vector<int> coverage;                  // sequences through the node
+    int n_seqs = 0;
+
+    int add_node(char c) {
+        letter.push_back(c); in.emplace_back(); out.emplace_back(); aligned.emplace_back();
+        coverage.push_back(0);
+        return (int)letter.size() - 1;
+    }
+    void add_edge(int a, int b, long long w) {
+        for (int e : out[a]) if (edges[e].to == b) { edges[e].w += w; return; }
+        edges.push_back({a, b, w});
+        out[a].push_back((int)edges.size() - 1);
+        in[b].push_back((int)edges.size() - 1);
+    }
+    // chain of new nodes for seq[b, e); returns first node or -1
+    int add_chain(const char *s, const int *wt, int b, int e) {
+        if (b >= e) return -1;
+        int first = add_node(s[b]);
+        coverage[first]++;
+        int prev = first;
+        for (int i = b + 1; i < e; ++i) {
+            int v = add_node(s[i]);
+            coverage[v]++;
+            add_edge(prev, v, (long long)wt[i - 1] + wt[i]);
+            prev = v;
+        }
+        return first;
+    }
+    // depth-first topological sort keeping aligned nodes adjacent
+    void topo_sort() {
+        const int n = (int)letter.size();
+        order.clear();
+        std::vector<uint8_t> mark(n, 0), check(n, 1);
+        std::vector<int> st;
+        for (int i = 0; i < n; ++i) {
+            if (mark[i]) continue;
+            st.push_back(i);
+            while (!st.empty()) {
+                int v = st.back();
+                bool ok = true;
+                if (mark[v] != 2) {
+                    for (int e : in[v]) if (mark[edges[e].from] != 2) { st.push_back(edges[e].from); ok = false; }
+                    if (check[v]) for (int a : aligned[v]) if (mark[a] != 2) { st.push_back(a); check[a] = 0; ok = false; }
+                    if (ok) {
+                        mark[v] = 2;
+                        if (check[v]) { order.push_back(v); for (int a : aligned[v]) order.push_back(a); }
+                    } else mark[v] = 1;
+                }
+                if (ok) st.pop_back();
+            }
+        }
+        rank.assign(n, 0);
+        for (int r = 0; r < n; ++r) rank[order[r]] = r;
+    }
+};
+
+struct Pair { int node, pos; };
+
+// mode 0 = local, 1 = global (both with linear gap g)
+static std::vector<Pair> align(const Graph &G, const char *s, int L, int mode, int m, int x, int g)
+{
+    const int V = (int)G.letter.size();
+    std::vector<Pair> aln;
+    if (V == 0 || L == 0) return aln;
+    const int NEG = INT_MIN / 4;
+    std::vector<int> H((size_t)(V + 1) * (L + 1), 0);
+    auto at = [&](int r, int j) -> int & { return H[(size_t)r * (L + 1) + j]; };
+    if (mode == 1) {
+        for (int j = 1; j <= L; ++j) at(0, j) = j * g;
+    }
+    int best = mode == 0 ? 0 : NEG, bi = 0, bj = 0;
+    for (int r = 0; r < V; ++r) {
+        const int v = G.order[r];
+        const char c = G.letter[v];
+        const int row = r + 1;
+        if (mode == 1) {
+            int p = NEG;
+            if (G.in[v].empty()) p = 0;
+            for (int e : G.in[v]) p = std::max(p, at(G.rank[G.edges[e].from] + 1, 0));
+            at(row, 0) = p + g;
+        }
+        for (int j = 1; j <= L; ++j) {
+            const int sc = (c == s[j - 1]) ? m : x;
+            int h = NEG;
+            if (G.in[v].empty()) {
+                h = std::max(at(0, j - 1) + sc, at(0, j) + g);
+            } else {
+                for (int e : G.in[v]) {
+                    const int pr = G.rank[G.edges[e].from] + 1;
+                    h = std::max(h, std::max(at(pr, j - 1) + sc, at(pr, j) + g));
+                }
+            }
+            h = std::max(h, at(row, j - 1) + g);
+            if (mode == 0) {
+                if (h < 0) h = 0;
+                if (h > best) { best = h; bi = row; bj = j; }
+            }
+            at(row, j) = h;
+        }
+        if (mode == 1 && G.out[v].empty()) {
+            if (at(row, L) > best) { best = at(row, L); bi = row; bj = L; }
+        }
+    }
+    if (mode == 0 && best == 0) return aln;
+    // traceback
+    int i = bi, j = bj;
+    std::vector<Pair> rev;
+    while ((mode == 0) ? (at(i, j) != 0) : (i != 0 || j != 0)) {
+        const int h = at(i, j);
+        bool done = false;
+        if (i != 0 && j != 0) {
+            const int v = G.order[i - 1];
+            const int sc = (G.letter[v] == s[j - 1]) ? m : x;
+            if (G.in[v].empty()) {
+                if (h == at(0, j - 1) + sc) { rev.push_back({v, j - 1}); i = 0; --j; done = true; }
+            } else {
+                for (int e : G.in[v]) {
+                    const int pr = G.rank[G.edges[e].from] + 1;
+                    if (h == at(pr, j - 1) + sc) { rev.push_back({v, j - 1}); i = pr; --j; done = true; break; }
+                }
+            }
+        }
+        if (!done && i != 0) {
+            const int v = G.order[i - 1];
+            if (G.in[v].empty()) {
+                if (h == at(0, j) + g) { rev.push_back({v, -1}); i = 0; done = true; }
+            } else {
+                for (int e : G.in[v]) {
+                    const int pr = G.rank[G.edges[e].from] + 1;
+                    if (h == at(pr, j) + g) { rev.push_back({v, -1}); i = pr; done = true; break; }
+                }
+            }
+        }
+        if (!done && j != 0) {
+            if (h == at(i, j - 1) + g) { rev.push_back({-1, j - 1}); --j; done = true; }
+        }
+        if (!done) break;   // cannot happen for a consistent matrix
+    }
+    aln.assign(rev.rbegin(), rev.rend());
+    return aln;
+}
+
+static void add_alignment(Graph &G, const std::vector<Pair> &aln, const char *s, const int *wt, int L)
+{
+    if (L == 0) return;
+    std::vector<int> valid;
+    for (const Pair &p : aln) if (p.pos >= 0) valid.push_back(p.pos);
+    if (valid.empty()) {
+        G.add_chain(s, wt, 0, L);
+        G.n_seqs++;
+        G.topo_sort();
+        return;
+    }
+    const int before = (int)G.letter.size();
+    G.add_chain(s, wt, 0, valid.front());
+    int head = ((int)G.letter.size() == before) ? -1 : (int)G.letter.size() - 1;
+    int tail = G.add_chain(s, wt, valid.back() + 1, L);
+    long long prev_w = head == -1 ? 0 : wt[valid.front() - 1];
+    for (const Pair &p : aln) {
+        if (p.pos < 0) continue;
+        const char c = s[p.pos];
+        int node;
+        if (p.node < 0) {
+            node = G.add_node(c);
+        } else if (G.letter[p.node] == c) {
+            node = p.node;
+        } else {
+            node = -1;
+            for (int a : G.aligned[p.node]) if (G.letter[a] == c) { node = a; break; }
+            if (node < 0) {
+                node = G.add_node(c);
+                for (int a : G.aligned[p.node]) { G.aligned[node].push_back(a); G.aligned[a].push_back(node); }
+                G.aligned[node].push_back(p.node);
+                G.aligned[p.node].push_back(node);
+            }
+        }
+        G.coverage[node]++;
+        if (head != -1) G.add_edge(head, node, prev_w + wt[p.pos]);
+        head = node;
+        prev_w = wt[p.pos];
+    }
+    if (tail != -1) G.add_edge(head, tail, prev_w + wt[valid.back() + 1]);
+    G.n_seqs++;
+    G.topo_sort();
+}
+
+static std::vector<int> heaviest_bundle(const Graph &G)
+{
+    const int V = (int)G.letter.size();
+    std::vector<int> path;
+    if (V == 0) return path;
+    std::vector<long long> score(V, -1);
+    std::vector<int> pred(V, -1);
+    auto relax = [&](int v, bool skip_dead) {
+        for (int e : G.in[v]) {
+            const Edge &E = G.edges[e];
+            if (skip_dead && score[E.from] == -1) continue;
+            if (score[v] < E.w || (score[v] == E.w && pred[v] != -1 && score[pred[v]] <= score[E.from])) {
+                score[v] = E.w; pred[v] = E.from;
+            }
+        }
+        if (pred[v] != -1) score[v] += score[pred[v]];
+    };
+    int best = G.order[0];
+    for (int r = 0; r < V; ++r) {
+        int v = G.order[r];
+        relax(v, false);
+        if (score[best] < score[v]) best = v;
+    }
+    // complete the branch to a sink
+    while (!G.out[best].empty()) {
+        const int r0 = G.rank[best];
+        for (int e : G.out[best])
+            for (int e2 : G.in[G.edges[e].to])
+                if (G.edges[e2].from != best) score[G.edges[e2].from] = -1;
+        long long ms = 0; int mid = -1;
+        for (int r = r0 + 1; r < V; ++r) {
+            int v = G.order[r];
+            score[v] = -1; pred[v] = -1;
+            relax(v, true);
+            if (ms < score[v]) { ms = score[v]; mid = v; }
+        }
+        if (mid < 0) break;
+        best = mid;
+    }
+    while (best != -1) { path.push_back(best); best = pred[best]; }
+    std::reverse(path.begin(), path.end());
+    return path;
+}
+
+}  // namespace
+
+extern "C" {
+
+/*
+ * POA consensus of n sequences added in the given order. quals may be NULL (all weights 1) or
+ * hold PHRED+33 strings (weight = q - 33; an empty string means weight 0 for that sequence, which
+ * is how a racon window treats its backbone). mode 0 local / 1 global; linear gap g (< 0).
+ * trim != 0 applies racon's coverage trimming to the consensus ends (coverage >= (n-1)/2).
+ * Returns the consensus length (written to out, capacity cap) or -1.
+ */
+int oracle_poa_consensus(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                         int trim, char *out, int cap, int *n_nodes_out)
+{
+    Graph G;
+    std::vector<int> wt;
+    for (int i = 0; i < n; ++i) {
+        const int L = (int)strlen(seqs[i]);
+        wt.assign(L, 1);
+        if (quals) {
+            const int ql = (int)strlen(quals[i]);
+            for (int t = 0; t < L; ++t) wt[t] = (t < ql) ? (int)quals[i][t] - 33 : 0;
+        }
+        std::vector<Pair> aln;
+        if (!G.letter.empty()) aln = align(G, seqs[i], L, mode, m, x, g);
+        add_alignment(G, aln, seqs[i], wt.data(), L);
+    }
+    std::vector<int> path = heaviest_bundle(G);
+    int b = 0, e = (int)path.size();
+    if (trim) {
+        const int need = (G.n_seqs - 1) / 2;
+        while (b < e && G.coverage[path[b]] < need) ++b;
+        while (e > b && G.coverage[path[e - 1]] < need) --e;
+        if (b >= e) { b = 0; e = (int)path.size(); }
+    }
+    if (e - b + 1 > cap) return -1;
+    for (int i = b; i < e; ++i) out[i - b] = G.letter[path[i]];
+    out[e - b] = 0;
+    if (n_nodes_out) *n_nodes_out = (int)G.letter.size();
+    return e - b;
+}
+
+}  // extern "C"

@@ -40,6 +40,23 @@ def _check_minimizers(eng, seqs, k, w):
 def test_k1_minimizers_fixtures(eng, tag, k, w):
     seqs = [s for _a, s, _q in scenario_reads(tag)]
     _check_minimizers(eng, seqs, k, w)
+    eng.set_option(1, 1)                # the generic warp-per-read kernel must agree as well
+    try:
+        _check_minimizers(eng, seqs, k, w)
+    finally:
+        eng.set_option(1, 0)
+
+
+@pytest.mark.parametrize("k,w", [(13, 20), (12, 19), (5, 12), (2, 9)])
+def test_k1_fast_kernel_window8(eng, k, w):
+    """Shapes served by the thread-per-read kernel (w-k+1 == 8), incl. repeats and odd lengths."""
+    rng = np.random.default_rng(k * 100 + w)
+    seqs = ["ACACACACACACACACACACACACACACACACACAC" * 3, "ACGT" * 40, "AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAC",
+            "A" * 100 + "C" * 100 + "G" * 5 + "ACGTTGCA" * 9]
+    for n in list(range(1, 140)) + [255, 256, 257, 1000, 3001]:
+        p = rng.dirichlet([0.5, 0.5, 0.5, 0.5])
+        seqs.append("".join(rng.choice(list("ACGT"), size=n, p=p)))
+    _check_minimizers(eng, seqs, k, w)
 
 
 def test_k1_minimizers_edge_cases(eng):
