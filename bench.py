@@ -331,7 +331,7 @@ def run_ours(args):
                        "(host orchestrates the greedy pass); device-event sum reported as device_ms_per_step",
                        "l2": "inputs_exceed_l2 (ASCII+packed reads + minimizers = %.0f MB per GPU)" %
                              ((offsets[hi] - offsets[lo]) * 2.25 / 1e6 + n_mine * 119 * 8 / 1e6),
-                       "tile_reads": args.tile or 4096},
+                       "tile_reads": args.tile or 65536},
             "device_ms_per_step": dev_ms / args.steps,
             "phase_ms_per_step": {k_: v / args.steps for k_, v in phase.items()},
             "e2e": {"value": e2e_v, "unit": "reads/s",

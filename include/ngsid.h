@@ -138,6 +138,46 @@ int ngsid_sg_block_align(ngsid_ctx *ctx, const int32_t *read_a, const int32_t *r
                          const int32_t *open, const int32_t *match_id, int64_t n_pairs, int k,
                          int32_t *out_count, int32_t *out_score);
 
+/* ---- K4 paths: alignment score / identity / window breaking points ---------------------------
+ * Replaces: consensus.parasail_alignment + highest_aln_identity (modules/consensus.py:58-73,
+ * 129-145: identity = equal columns / all columns of the semi-global alignment, open 3) and the
+ * read-to-draft mapping that run_racon obtains from minimap2 (modules/consensus.py:121), in the
+ * form racon consumes it: per 500-base window of the target the first/last aligned (=/X) column.
+ * a[i] is the row sequence (s1), b[i] the column sequence (s2); an index >= 0 names an uploaded
+ * read, an index < 0 names auxiliary sequence -index-1 of (aux_seq, aux_off) (host buffers, e.g.
+ * consensus strings). out_win (optional) receives 16 windows x 4 int32 per pair:
+ * (q_first, q_last_exclusive, t_first, t_last_exclusive), -1 when the window has no aligned column. */
+int ngsid_sg_align_paths(ngsid_ctx *ctx, const int32_t *a, const int32_t *b, const int32_t *open,
+                         int64_t n_pairs, const uint8_t *aux_seq, const int64_t *aux_off, int64_t n_aux,
+                         int window, int32_t *out_score, int32_t *out_match, int32_t *out_cols,
+                         int32_t *out_win);
+
+/* ---- K5: partial-order-alignment consensus ---------------------------------------------------
+ * Replaces: the spoa call of consensus.run_spoa (modules/consensus.py:83-92: local alignment,
+ * match 5, mismatch -4, linear gap -2, quality weights, heaviest-bundle consensus) and the
+ * per-window POA inside racon (consensus.run_racon, modules/consensus.py:107-126: global,
+ * 3 / -5 / -4, backbone without weight, coverage-trimmed consensus).
+ * Jobs are independent (one thread block each). Job j consists of layers
+ * [job_off[j], job_off[j+1]) added in that order; layer l is bases [layer_begin[l],
+ * layer_begin[l]+layer_len[l]) of uploaded read layer_src[l] (weights = quality - 33) or, when
+ * layer_src[l] < 0, of auxiliary sequence -layer_src[l]-1 (weight 0).
+ * out_seq holds n_jobs rows of out_stride bytes; out_len[j] = consensus length.
+ * max_nodes bounds the graph of one job (0 = 32 x longest layer, at least 4096); a job that would
+ * exceed it fails the call with NGSID_EUNSUPPORTED (no silent truncation).                      */
+typedef struct {
+    int32_t mode;        /* 0 local (spoa -l 0), 1 global (racon windows) */
+    int32_t match, mismatch, gap;
+    int32_t trim;        /* racon's coverage trimming of the consensus ends */
+    int32_t max_nodes;
+    int32_t reserved[2];
+} ngsid_poa_params;
+
+int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                        const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                        const int32_t *layer_len, const uint8_t *aux_seq, const int64_t *aux_off,
+                        int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                        int32_t *out_nodes);
+
 #ifdef __cplusplus
 }
 #endif

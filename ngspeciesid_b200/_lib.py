@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libngsid.so")
 EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last_error",
            "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
-           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_cluster", "ngsid_sg_block_align"]
+           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus"]
 
 
 class ClusterParams(ctypes.Structure):
@@ -20,6 +20,12 @@ class ClusterParams(ctypes.Structure):
                 ("mapped_threshold", ctypes.c_double), ("aligned_threshold", ctypes.c_double),
                 ("max_gap", ctypes.c_int32 * 225), ("tile_reads", ctypes.c_int32),
                 ("reserved", ctypes.c_int32 * 7)]
+
+
+class PoaParams(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("match", ctypes.c_int32), ("mismatch", ctypes.c_int32),
+                ("gap", ctypes.c_int32), ("trim", ctypes.c_int32), ("max_nodes", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 2)]
 
 
 class ClusterStats(ctypes.Structure):
@@ -68,6 +74,8 @@ def load():
     lib.ngsid_get_quality_stats.argtypes = [vp, i64, i64, vp, vp, vp]
     lib.ngsid_cluster.argtypes = [vp, P(ClusterParams), vp, i64, vp, i64, vp, vp, vp, P(ClusterStats)]
     lib.ngsid_sg_block_align.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.ngsid_sg_align_paths.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp]
+    lib.ngsid_poa_consensus.argtypes = [vp, P(PoaParams), i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

@@ -6,6 +6,8 @@
 #include "k1_minimizers.cuh"
 #include "k2_map.cuh"
 #include "k4_align.cuh"
+#include "k4_trace.cuh"
+#include "k5_poa.cuh"
 
 static const size_t SMEM_BUDGET = 200 * 1024;
 
@@ -51,6 +53,7 @@ extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
 {
     if (!ctx) return NGSID_EINVAL;
     if (option == 1) { ctx->force_generic_k1 = value != 0; ctx->have_min = false; return NGSID_OK; }
+    if (option == 2) { ctx->use_payload_k4 = value != 0; return NGSID_OK; }
     return fail(ctx, NGSID_EINVAL, "unknown option");
 }
 
@@ -65,7 +68,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
                       &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
-                      &ctx->d_newslots, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+                      &ctx->d_newslots, &ctx->d_poa_arena, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
     cudaEventDestroy(ctx->ev0);
@@ -362,6 +365,54 @@ static int k4_launch(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const
     return NGSID_OK;
 }
 
+
+// ---- K4 trace variant: DP with packed trace + traceback, processed in chunks of trace slots ----
+static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const int32_t *po, const int32_t *pm,
+                   int stride, int64_t n_pairs, int k, int max_n1, int max_n2, bool have_aux,
+                   int32_t *out_count, int32_t *out_score, int32_t *out_match, int32_t *out_cols,
+                   K4TWindow *out_win, int window)
+{
+    if (n_pairs == 0) return NGSID_OK;
+    int n2cap = ((max_n2 + 15) / 16) * 16 + 16;
+    size_t per_warp = k4t_smem_per_warp(n2cap);
+    int wpb = (int)std::min<size_t>(4, SMEM_BUDGET / per_warp);
+    if (wpb < 1) return fail(ctx, NGSID_EUNSUPPORTED, "sequence too long for the K4 shared-memory row buffer");
+    size_t smem = per_warp * wpb;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k4t_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int bps = 1;
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k4t_dp_kernel, wpb * 32, smem));
+    bps = std::max(1, bps);
+    const size_t slot_words = k4t_trace_words(max_n1, max_n2);
+    const size_t budget = (size_t)4 << 30;
+    int64_t slots = (int64_t)std::max<size_t>(1, budget / (slot_words * 4));
+    slots = std::min<int64_t>(slots, n_pairs);
+    CUDA_TRY(ctx, ctx->d_trace.ensure((size_t)slots * slot_words * 4));
+    CUDA_TRY(ctx, ctx->d_ends.ensure((size_t)slots * sizeof(K4TEnd)));
+    K4TSeqs Q = {ctx->d_seq.as<uint8_t>(), ctx->d_off.as<int64_t>(),
+                 have_aux ? ctx->d_auxseq.as<uint8_t>() : nullptr, have_aux ? ctx->d_aoff.as<int64_t>() : nullptr};
+    for (int64_t p0 = 0; p0 < n_pairs; p0 += slots) {
+        const int64_t c = std::min<int64_t>(slots, n_pairs - p0);
+        int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c + wpb - 1) / wpb, (int64_t)ctx->sm_count * bps));
+        k4t_dp_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(Q, pa, pb, po, stride, p0, c, n2cap,
+                                                               ctx->d_trace.as<uint32_t>(), slot_words,
+                                                               ctx->d_ends.as<K4TEnd>());
+        KERNEL_CHECK(ctx);
+        k4t_traceback_kernel<<<(unsigned)((c + 127) / 128), 128, 0, ctx->stream>>>(
+            Q, pa, pb, pm, stride, p0, c, k, ctx->d_trace.as<uint32_t>(), slot_words, ctx->d_ends.as<K4TEnd>(),
+            out_count, out_score, out_match, out_cols, out_win, window);
+        KERNEL_CHECK(ctx);
+    }
+    return NGSID_OK;
+}
+
+static int k4_dispatch(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const int32_t *po, const int32_t *pm,
+                       int stride, int64_t n_pairs, int k, int32_t *out_count, int32_t *out_score)
+{
+    if (ctx->use_payload_k4) return k4_launch(ctx, pa, pb, po, pm, stride, n_pairs, k, out_count, out_score);
+    return k4t_run(ctx, pa, pb, po, pm, stride, n_pairs, k, ctx->max_len, ctx->max_len, false,
+                   out_count, out_score, nullptr, nullptr, nullptr, 500);
+}
+
 extern "C" int ngsid_sg_block_align(ngsid_ctx *ctx, const int32_t *read_a, const int32_t *read_b,
                                     const int32_t *open, const int32_t *match_id, int64_t n_pairs, int k,
                                     int32_t *out_count, int32_t *out_score)
@@ -387,12 +438,140 @@ extern "C" int ngsid_sg_block_align(ngsid_ctx *ctx, const int32_t *read_a, const
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pb.p, read_b, nb, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_po.p, open, nb, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pm.p, match_id, nb, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = k4_launch(ctx, ctx->d_pa.as<int32_t>(), ctx->d_pb.as<int32_t>(), ctx->d_po.as<int32_t>(),
-                       ctx->d_pm.as<int32_t>(), 1, n_pairs, k, ctx->d_k4cnt.as<int32_t>(), ctx->d_k4score.as<int32_t>());
+    int rc = k4_dispatch(ctx, ctx->d_pa.as<int32_t>(), ctx->d_pb.as<int32_t>(), ctx->d_po.as<int32_t>(),
+                         ctx->d_pm.as<int32_t>(), 1, n_pairs, k, ctx->d_k4cnt.as<int32_t>(), ctx->d_k4score.as<int32_t>());
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(out_count, ctx->d_k4cnt.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_score) CUDA_TRY(ctx, cudaMemcpyAsync(out_score, ctx->d_k4score.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NGSID_OK;
+}
+
+
+static int upload_aux(ngsid_ctx *ctx, const uint8_t *aux_seq, const int64_t *aux_off, int64_t n_aux)
+{
+    if (n_aux <= 0) return NGSID_OK;
+    if (!aux_seq || !aux_off || aux_off[0] != 0) return fail(ctx, NGSID_EINVAL, "bad auxiliary sequence arena");
+    CUDA_TRY(ctx, ctx->d_auxseq.ensure((size_t)aux_off[n_aux] + 64));
+    CUDA_TRY(ctx, ctx->d_aoff.ensure((size_t)(n_aux + 1) * sizeof(int64_t)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_auxseq.p, aux_seq, (size_t)aux_off[n_aux], cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_aoff.p, aux_off, (size_t)(n_aux + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    return NGSID_OK;
+}
+
+extern "C" int ngsid_sg_align_paths(ngsid_ctx *ctx, const int32_t *a, const int32_t *b, const int32_t *open,
+                                    int64_t n_pairs, const uint8_t *aux_seq, const int64_t *aux_off, int64_t n_aux,
+                                    int window, int32_t *out_score, int32_t *out_match, int32_t *out_cols,
+                                    int32_t *out_win)
+{
+    if (!ctx || n_pairs < 0 || (n_pairs > 0 && (!a || !b || !open)) || window < 1) return NGSID_EINVAL;
+    if (n_pairs == 0) return NGSID_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int max1 = 1, max2 = 1;
+    auto seqlen = [&](int r, int64_t &L) -> bool {
+        if (r >= 0) { if (r >= ctx->n_reads) return false; L = ctx->h_off[r + 1] - ctx->h_off[r]; }
+        else { int64_t x = -(int64_t)r - 1; if (x >= n_aux) return false; L = aux_off[x + 1] - aux_off[x]; }
+        return true;
+    };
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        int64_t l1 = 0, l2 = 0;
+        if (!seqlen(a[i], l1) || !seqlen(b[i], l2)) return fail(ctx, NGSID_EINVAL, "pair index out of range");
+        if (l1 < 1 || l2 < 1) return fail(ctx, NGSID_EINVAL, "empty sequence in alignment pair");
+        if (out_win && (l2 + window - 1) / window > K4T_MAXWIN) return fail(ctx, NGSID_EUNSUPPORTED, "target longer than 16 windows");
+        max1 = std::max<int>(max1, (int)l1); max2 = std::max<int>(max2, (int)l2);
+    }
+    int rc = upload_aux(ctx, aux_seq, aux_off, n_aux);
+    if (rc) return rc;
+    size_t nb = (size_t)n_pairs * sizeof(int32_t);
+    CUDA_TRY(ctx, ctx->d_pa.ensure(nb)); CUDA_TRY(ctx, ctx->d_pb.ensure(nb)); CUDA_TRY(ctx, ctx->d_po.ensure(nb));
+    CUDA_TRY(ctx, ctx->d_k4score.ensure(nb)); CUDA_TRY(ctx, ctx->d_match.ensure(nb)); CUDA_TRY(ctx, ctx->d_cols.ensure(nb));
+    if (out_win) CUDA_TRY(ctx, ctx->d_win.ensure((size_t)n_pairs * K4T_MAXWIN * sizeof(K4TWindow)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pa.p, a, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_pb.p, b, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_po.p, open, nb, cudaMemcpyHostToDevice, ctx->stream));
+    rc = k4t_run(ctx, ctx->d_pa.as<int32_t>(), ctx->d_pb.as<int32_t>(), ctx->d_po.as<int32_t>(), nullptr, 1, n_pairs,
+                 13, max1, max2, n_aux > 0, nullptr, ctx->d_k4score.as<int32_t>(), ctx->d_match.as<int32_t>(),
+                 ctx->d_cols.as<int32_t>(), out_win ? ctx->d_win.as<K4TWindow>() : nullptr, window);
+    if (rc) return rc;
+    if (out_score) CUDA_TRY(ctx, cudaMemcpyAsync(out_score, ctx->d_k4score.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_match) CUDA_TRY(ctx, cudaMemcpyAsync(out_match, ctx->d_match.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_cols) CUDA_TRY(ctx, cudaMemcpyAsync(out_cols, ctx->d_cols.p, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_win) CUDA_TRY(ctx, cudaMemcpyAsync(out_win, ctx->d_win.p, (size_t)n_pairs * K4T_MAXWIN * sizeof(K4TWindow), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return NGSID_OK;
+}
+
+
+// ================================================================================ K5
+extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                                   const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                                   const int32_t *layer_len, const uint8_t *aux_seq, const int64_t *aux_off,
+                                   int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                                   int32_t *out_nodes)
+{
+    if (!ctx || !params || n_jobs < 0) return NGSID_EINVAL;
+    if (n_jobs == 0) return NGSID_OK;
+    if (!job_off || !layer_src || !layer_begin || !layer_len || !out_seq || !out_len || out_stride < 1) return NGSID_EINVAL;
+    if (params->gap >= 0) return fail(ctx, NGSID_EINVAL, "gap must be negative");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_layers = job_off[n_jobs];
+    int Lmax = 1;
+    for (int64_t l = 0; l < n_layers; ++l) {
+        const int src = layer_src[l];
+        int64_t len;
+        if (src >= 0) { if (src >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "layer read out of range"); len = ctx->h_off[src + 1] - ctx->h_off[src]; }
+        else { int64_t x = -(int64_t)src - 1; if (x >= n_aux) return fail(ctx, NGSID_EINVAL, "layer aux out of range"); len = aux_off[x + 1] - aux_off[x]; }
+        if (layer_begin[l] < 0 || layer_len[l] < 0 || (int64_t)layer_begin[l] + layer_len[l] > len) return fail(ctx, NGSID_EINVAL, "layer range out of bounds");
+        Lmax = std::max(Lmax, (int)layer_len[l]);
+    }
+    int rc = upload_aux(ctx, aux_seq, aux_off, n_aux);
+    if (rc) return rc;
+    const int Vcap = params->max_nodes > 0 ? std::max(params->max_nodes, Lmax + 16) : std::max(4096, 32 * Lmax);
+    const int Ecap = Vcap * 6, Acap = Vcap * 6, Scap = Vcap * 14;
+    const size_t gbytes = (poa_graph_bytes(Vcap, Ecap, Acap, Scap, Lmax) + 255) / 256 * 256;
+    const size_t h_words = ((size_t)(Vcap + 1) * (size_t)(Lmax + 1) + 63) / 64 * 64;
+    int slots = (int)std::min<int64_t>(n_jobs, ctx->sm_count);
+    // keep the DP arenas within 48 GB
+    while (slots > 1 && (double)slots * (double)(h_words * 4 + gbytes) > 48e9) slots /= 2;
+    CUDA_TRY(ctx, ctx->d_poa_arena.ensure(gbytes * slots));
+    CUDA_TRY(ctx, ctx->d_poa_h.ensure(h_words * 4 * slots));
+    CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)n_jobs * out_stride));
+    CUDA_TRY(ctx, ctx->d_poa_len.ensure((size_t)n_jobs * 4));
+    CUDA_TRY(ctx, ctx->d_poa_nodes.ensure((size_t)n_jobs * 4));
+    CUDA_TRY(ctx, ctx->d_poa_err.ensure(64));
+    CUDA_TRY(ctx, ctx->d_job_off.ensure((size_t)(n_jobs + 1) * 8));
+    CUDA_TRY(ctx, ctx->d_lsrc.ensure((size_t)n_layers * 4 + 16));
+    CUDA_TRY(ctx, ctx->d_lbeg.ensure((size_t)n_layers * 4 + 16));
+    CUDA_TRY(ctx, ctx->d_llen.ensure((size_t)n_layers * 4 + 16));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_poa_err.p, 0, 64, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_job_off.p, job_off, (size_t)(n_jobs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lsrc.p, layer_src, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lbeg.p, layer_begin, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_llen.p, layer_len, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
+    K5Args A;
+    A.n_jobs = n_jobs; A.job_off = ctx->d_job_off.as<int64_t>();
+    A.layer_src = ctx->d_lsrc.as<int32_t>(); A.layer_begin = ctx->d_lbeg.as<int32_t>(); A.layer_len = ctx->d_llen.as<int32_t>();
+    A.seq = ctx->d_seq.as<uint8_t>(); A.qual = ctx->d_qual.as<uint8_t>(); A.off = ctx->d_off.as<int64_t>();
+    A.aux = n_aux > 0 ? ctx->d_auxseq.as<uint8_t>() : nullptr; A.aoff = n_aux > 0 ? ctx->d_aoff.as<int64_t>() : nullptr;
+    A.mode = params->mode; A.m = params->match; A.x = params->mismatch; A.g = params->gap; A.trim = params->trim;
+    A.arena = ctx->d_poa_arena.as<uint8_t>(); A.graph_bytes = gbytes;
+    A.Vcap = Vcap; A.Ecap = Ecap; A.Acap = Acap; A.Scap = Scap; A.Lmax = Lmax;
+    A.H = ctx->d_poa_h.as<int32_t>(); A.h_words = h_words;
+    A.out = ctx->d_poa_out.as<uint8_t>(); A.out_stride = out_stride; A.out_len = ctx->d_poa_len.as<int32_t>();
+    A.out_nodes = ctx->d_poa_nodes.as<int32_t>(); A.err = ctx->d_poa_err.as<int32_t>();
+    k5_poa_kernel<<<slots, K5_THREADS, 0, ctx->stream>>>(A);
+    KERNEL_CHECK(ctx);
+    int err = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_seq, ctx->d_poa_out.p, (size_t)n_jobs * out_stride, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_len, ctx->d_poa_len.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_nodes) CUDA_TRY(ctx, cudaMemcpyAsync(out_nodes, ctx->d_poa_nodes.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "POA graph capacity exceeded (code %d, max_nodes %d): raise max_nodes or cap the reads per consensus", err, Vcap);
+        return fail(ctx, NGSID_EUNSUPPORTED, msg);
+    }
     return NGSID_OK;
 }
 
@@ -560,8 +739,8 @@ int ClusterRun::run_map(const int32_t *d_list, int n_list)
         if (nreq == 0) return NGSID_OK;
         const AlignRequest *rq = ctx->d_req.as<AlignRequest>();
         ev_begin(ctx, 4);
-        int rc = k4_launch(ctx, &rq->read_a, &rq->read_b, &rq->open, &rq->match_id, 6, nreq, ctx->k,
-                           ctx->d_k4cnt.as<int32_t>(), nullptr);
+        int rc = k4_dispatch(ctx, &rq->read_a, &rq->read_b, &rq->open, &rq->match_id, 6, nreq, ctx->k,
+                             ctx->d_k4cnt.as<int32_t>(), nullptr);
         ev_end(ctx);
         if (rc) return rc;
         st.n_alignments += nreq;
@@ -691,7 +870,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     rc = R.insert_slots(0, R.n_slots);
     if (rc) return cleanup(rc);
 
-    const int tmax = params->tile_reads > 0 ? params->tile_reads : 4096;
+    const int tmax = params->tile_reads > 0 ? params->tile_reads : 65536;
     int T = std::min(32, tmax);
     int pos = 0;
     std::vector<int32_t> U, h_list;

@@ -9,7 +9,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import ClusterParams, ClusterStats, NgsidError, as_array, ptr
+from ._lib import ClusterParams, ClusterStats, NgsidError, PoaParams, as_array, ptr
 
 # PHRED char -> capped error probability, exactly the reference's table (modules/cluster.py:233)
 PHRED_P = np.array([min(10 ** (-(c - 33) / 10.0), 0.79433) for c in range(128)], dtype=np.float64)
@@ -110,6 +110,8 @@ class Engine(object):
         self._check(self.lib.ngsid_upload_reads(self.h, ptr(seq), ptr(qual), ptr(offsets), n))
         self.n_reads = n
         self.offsets = offsets
+        self.h_seq, self.h_qual = seq, qual
+        self._qcs = None
         self._q_done = False
 
     def upload_records(self, records):
@@ -189,6 +191,53 @@ class Engine(object):
         score = np.zeros(len(a), dtype=np.int32) if want_score else None
         self._check(self.lib.ngsid_sg_block_align(self.h, ptr(a), ptr(b), ptr(o), ptr(m), len(a), k, ptr(cnt), ptr(score)))
         return (cnt, score) if want_score else cnt
+
+    def sg_align_paths(self, a, b, open_pen, aux=None, window=500, want_windows=False):
+        """Semi-global alignments of rows a[i] against columns b[i]; indices < 0 name aux strings.
+        Returns (score, n_match, n_cols[, windows (n,16,4)])."""
+        a, b = as_array(a, np.int32), as_array(b, np.int32)
+        o = as_array(open_pen, np.int32)
+        n = len(a)
+        aux_seq, aux_off, n_aux = None, None, 0
+        if aux:
+            enc = [s.encode("ascii") for s in aux]
+            aux_off = np.zeros(len(enc) + 1, dtype=np.int64)
+            np.cumsum([len(s) for s in enc], out=aux_off[1:])
+            aux_seq = np.frombuffer(b"".join(enc), dtype=np.uint8)
+            n_aux = len(enc)
+        score = np.zeros(n, dtype=np.int32)
+        nmatch = np.zeros(n, dtype=np.int32)
+        ncols = np.zeros(n, dtype=np.int32)
+        win = np.zeros((n, 16, 4), dtype=np.int32) if want_windows else None
+        self._check(self.lib.ngsid_sg_align_paths(self.h, ptr(a), ptr(b), ptr(o), n, ptr(aux_seq), ptr(aux_off), n_aux,
+                                                  window, ptr(score), ptr(nmatch), ptr(ncols), ptr(win)))
+        return (score, nmatch, ncols, win) if want_windows else (score, nmatch, ncols)
+
+    def poa_consensus(self, job_off, layer_src, layer_begin, layer_len, aux=None, mode=0, match=5,
+                      mismatch=-4, gap=-2, trim=False, max_nodes=0):
+        """K5: one POA consensus per job. Layers index uploaded reads (>= 0) or aux strings (< 0).
+        Returns (list of consensus strings, node counts)."""
+        job_off = as_array(job_off, np.int64)
+        src, beg, ln = as_array(layer_src, np.int32), as_array(layer_begin, np.int32), as_array(layer_len, np.int32)
+        n_jobs = len(job_off) - 1
+        if n_jobs <= 0:
+            return [], np.zeros(0, dtype=np.int32)
+        aux_seq, aux_off, n_aux = None, None, 0
+        if aux:
+            enc = [s.encode("ascii") for s in aux]
+            aux_off = np.zeros(len(enc) + 1, dtype=np.int64)
+            np.cumsum([len(s) for s in enc], out=aux_off[1:])
+            aux_seq = np.frombuffer(b"".join(enc) + b"\0", dtype=np.uint8)
+            n_aux = len(enc)
+        p = PoaParams()
+        p.mode, p.match, p.mismatch, p.gap, p.trim, p.max_nodes = mode, match, mismatch, gap, 1 if trim else 0, max_nodes
+        stride = 4 * int(ln.max() if len(ln) else 1) + 64
+        out = np.zeros((n_jobs, stride), dtype=np.uint8)
+        out_len = np.zeros(n_jobs, dtype=np.int32)
+        nodes = np.zeros(n_jobs, dtype=np.int32)
+        self._check(self.lib.ngsid_poa_consensus(self.h, ctypes.byref(p), n_jobs, ptr(job_off), ptr(src), ptr(beg), ptr(ln),
+                                                 ptr(aux_seq), ptr(aux_off), n_aux, ptr(out), stride, ptr(out_len), ptr(nodes)))
+        return [out[j, :out_len[j]].tobytes().decode("ascii") for j in range(n_jobs)], nodes
 
     def set_option(self, option, value):
         self._check(self.lib.ngsid_set_option(self.h, option, value))

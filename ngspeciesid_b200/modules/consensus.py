@@ -1,0 +1,289 @@
+"""
+Drop-in for the reference's modules/consensus.py hot path (ksahlin/NGSpeciesID v0.3.1): the
+subprocess calls to spoa / minimap2 / racon are replaced by in-process CUDA kernels reached through
+libngsid.so (K5 partial-order alignment, K4 read-to-draft alignment). Function names, arguments,
+return values and the files written follow the reference (file:line cited per function).
+Medaka polishing (run_medaka, modules/consensus.py:94-104) is out of scope and not provided.
+"""
+import glob
+import logging
+import os
+import shutil
+
+import numpy as np
+
+from .. import engine as _engine
+from . import help_functions
+
+WINDOW = 500                     # racon's default window length
+_RC = bytes.maketrans(b"ACGT", b"TGCA")
+
+
+def reverse_complement(string):
+    """Reference: modules/consensus.py:75-81 (ACGT alphabet of this build)."""
+    return string.encode().translate(_RC)[::-1].decode()
+
+
+# ------------------------------------------------------------------------------------- array level
+def draft_consensus_batch(eng, read_lists, max_nodes=0):
+    """One spoa-equivalent consensus per list of uploaded-read indices (file order), all lists in
+    one launch (one thread block per list)."""
+    job_off = np.zeros(len(read_lists) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in read_lists], out=job_off[1:])
+    src = np.concatenate([np.asarray(r, dtype=np.int32) for r in read_lists]) if read_lists else np.zeros(0, np.int32)
+    lens = np.diff(eng.offsets)[src].astype(np.int32)
+    cons, nodes = eng.poa_consensus(job_off, src, np.zeros(len(src), dtype=np.int32), lens,
+                                    mode=0, match=5, mismatch=-4, gap=-2, trim=False, max_nodes=max_nodes)
+    return cons, nodes
+
+
+def _quality_prefix(eng):
+    if eng._qcs is None:
+        eng._qcs = np.concatenate([[0], np.cumsum(eng.h_qual.astype(np.int64) - 33)])
+    return eng._qcs
+
+
+def polish_round_batch(eng, targets, read_lists, rc_lists=None, max_nodes=0):
+    """One racon-equivalent round for every target at once. read_lists[t]: uploaded-read indices
+    polishing target t; rc_lists[t] (optional): for each of them the index of its uploaded reverse
+    complement, or -1 -- when given, a read is used in the orientation with the higher score."""
+    n_t = len(targets)
+    A, B = [], []
+    for t, rl in enumerate(read_lists):
+        A.extend(rl)
+        B.extend([-t - 1] * len(rl))
+    A = np.asarray(A, dtype=np.int32)
+    B = np.asarray(B, dtype=np.int32)
+    if len(A) == 0:
+        return list(targets)
+    score, _m, _c, win = eng.sg_align_paths(A, B, np.full(len(A), 3, dtype=np.int32), aux=targets,
+                                            window=WINDOW, want_windows=True)
+    if rc_lists is not None:
+        R = np.concatenate([np.asarray(r, dtype=np.int32) for r in rc_lists])
+        has = R >= 0
+        if has.any():
+            s2, _m2, _c2, w2 = eng.sg_align_paths(R[has], B[has], np.full(int(has.sum()), 3, dtype=np.int32),
+                                                  aux=targets, window=WINDOW, want_windows=True)
+            better = np.zeros(len(A), dtype=bool)
+            better[np.nonzero(has)[0]] = s2 > score[has]
+            idx = np.nonzero(has)[0]
+            take = s2 > score[has]
+            win[idx[take]] = w2[take]
+            A = A.copy()
+            A[idx[take]] = R[has][take]
+    tlen = np.array([len(t) for t in targets], dtype=np.int64)
+    tl = tlen[-B - 1]
+    qcs = _quality_prefix(eng)
+    roff = eng.offsets[A]
+    jobs, job_keys = [], []
+    layer_rows = []
+    n_pairs = len(A)
+    for w in range(16):
+        q0, q1, t0, t1 = win[:, w, 0], win[:, w, 1], win[:, w, 2], win[:, w, 3]
+        ws = w * WINDOW
+        wlen = np.minimum(WINDOW, tl - ws)
+        ok = (q0 >= 0) & (wlen > 0)
+        if not ok.any():
+            continue
+        seg = (q1 - q0).astype(np.int64)
+        ok &= ~(seg < 0.02 * wlen)
+        segc = np.maximum(seg, 1)
+        mean_q = (qcs[roff + np.maximum(q1, 0)] - qcs[roff + np.maximum(q0, 0)]) / segc.astype(np.float64)
+        ok &= ~(mean_q < 10.0)
+        off = 0.01 * wlen
+        b, e = t0 - ws, t1 - ws - 1
+        ok &= (b < off) & (e > wlen - off)
+        rows = np.nonzero(ok)[0]
+        if len(rows):
+            layer_rows.append(np.stack([(-B[rows] - 1).astype(np.int64), np.full(len(rows), w, dtype=np.int64), b[rows].astype(np.int64),
+                                        rows.astype(np.int64), A[rows].astype(np.int64), q0[rows].astype(np.int64), seg[rows]], axis=1))
+    out = []
+    if not layer_rows:
+        return list(targets)
+    L = np.concatenate(layer_rows)
+    # per (target, window): layers sorted by start, ties in read order
+    order = np.lexsort((L[:, 3], L[:, 2], L[:, 1], L[:, 0]))
+    L = L[order]
+    key = L[:, 0] * 16 + L[:, 1]
+    uniq, start, count = np.unique(key, return_index=True, return_counts=True)
+    job_off, src, beg, ln, job_key = [0], [], [], [], []
+    for u, s0, c in zip(uniq, start, count):
+        if c + 1 < 3:
+            continue
+        t, w = int(u // 16), int(u % 16)
+        ws = w * WINDOW
+        wlen = min(WINDOW, len(targets[t]) - ws)
+        src.append(-t - 1); beg.append(ws); ln.append(wlen)
+        rows = L[s0:s0 + c]
+        src.extend(rows[:, 4].tolist()); beg.extend(rows[:, 5].tolist()); ln.extend(rows[:, 6].tolist())
+        job_off.append(len(src))
+        job_key.append((t, w))
+    cons = {}
+    if job_key:
+        res, _nodes = eng.poa_consensus(job_off, src, beg, ln, aux=targets, mode=1, match=3, mismatch=-5, gap=-4,
+                                        trim=True, max_nodes=max_nodes)
+        cons = dict(zip(job_key, res))
+    for t, tgt in enumerate(targets):
+        parts = []
+        for w in range((len(tgt) + WINDOW - 1) // WINDOW):
+            parts.append(cons.get((t, w), tgt[w * WINDOW:(w + 1) * WINDOW]))
+        out.append("".join(parts))
+    return out
+
+
+def polish_batch(eng, targets, read_lists, iters, rc_lists=None, max_nodes=0):
+    for _ in range(iters):
+        targets = polish_round_batch(eng, targets, read_lists, rc_lists, max_nodes)
+    return targets
+
+
+# ------------------------------------------------------------------------------------- reference-shaped
+def _read_fastq(path):
+    with open(path, "r") as f:
+        return [(acc, seq, qual) for acc, (seq, qual) in help_functions.readfq(f)]
+
+
+def run_spoa(reads, spoa_out_file, spoa_path):
+    """Reference: modules/consensus.py:83-92. `reads` is a FASTQ path; the consensus is also left
+    in `spoa_out_file` as a 2-line FASTA (line 2 = sequence), `spoa_path` is ignored."""
+    recs = _read_fastq(reads)
+    eng = _engine.get_engine()
+    eng.upload_records([(s, q) for _a, s, q in recs])
+    cons, _n = draft_consensus_batch(eng, [list(range(len(recs)))])
+    with open(spoa_out_file, "w") as f:
+        f.write(">Consensus LN:i:{0} RC:i:{1} XC:f:1.000000\n{2}\n".format(len(cons[0]), len(recs), cons[0]))
+    return cons[0]
+
+
+def run_racon(reads_to_center, center_file, outfolder, cores, racon_iter):
+    """Reference: modules/consensus.py:107-126. Writes racon_polished_it_<i>.fasta per iteration and
+    consensus.fasta (2-line FASTA) into `outfolder`; reads of either strand are used in the
+    orientation that aligns better to the centre (what minimap2 decides in the reference)."""
+    recs = _read_fastq(reads_to_center)
+    with open(center_file) as f:
+        lines = f.readlines()
+    name, target = lines[0].strip()[1:], lines[1].strip()
+    eng = _engine.get_engine()
+    fwd = [(s, q) for _a, s, q in recs]
+    rc = [(reverse_complement(s), q[::-1]) for s, q in fwd]
+    eng.upload_records(fwd + rc)
+    n = len(fwd)
+    with open(os.path.join(outfolder, "stdout.txt"), "w") as log:
+        for i in range(racon_iter):
+            target = polish_round_batch(eng, [target], [list(range(n))], [list(range(n, 2 * n))])[0]
+            open(os.path.join(outfolder, "read_alignments_it_{0}.paf".format(i)), "w").close()
+            with open(os.path.join(outfolder, "racon_polished_it_{0}.fasta".format(i)), "w") as f:
+                f.write(">{0} LN:i:{1} RC:i:{2} XC:f:1.000000\n{3}\n".format(name, len(target), n, target))
+            log.write("iteration {0}: {1} bases\n".format(i, len(target)))
+        with open(os.path.join(outfolder, "consensus.fasta"), "w") as f:
+            f.write(">{0} LN:i:{1} RC:i:{2} XC:f:1.000000\n{3}\n".format(name, len(target), n, target))
+
+
+def highest_aln_identity(seq, seq2):
+    """Reference: modules/consensus.py:129-145: identity (equal columns / all columns) of the
+    semi-global alignment (open 3, extend 1) in the better of the two orientations."""
+    eng = _engine.get_engine()
+    if eng.n_reads == 0:
+        eng.upload_records([("ACGT", "5555")])
+    _s, m, c = eng.sg_align_paths([-1, -1], [-2, -3], [3, 3], aux=[seq, reverse_complement(seq2), seq2])
+    ident_rc = m[0] / float(c[0])
+    ident_fw = m[1] / float(c[1])
+    logging.debug("Rec comp orientation identity %: {0}".format(ident_rc))
+    logging.debug("Forward orientation identity %: {0}".format(ident_fw))
+    return max([ident_fw, ident_rc])
+
+
+def detect_reverse_complements(centers, rc_identity_threshold):
+    """Reference: modules/consensus.py:148-183, including its bookkeeping quirks (the inner loop does
+    not skip centres that were already merged, and re-binds `reads_path`)."""
+    filtered_centers = []
+    already_removed = set()
+    for i, (nr_reads_in_cl, c_id, seq, reads_path) in enumerate(centers):
+        all_reads = [reads_path] if type(reads_path) != list else reads_path
+        merged_nr_reads = nr_reads_in_cl
+        if c_id in already_removed:
+            continue
+        elif i == len(centers) - 1:
+            filtered_centers.append([merged_nr_reads, c_id, seq, all_reads])
+        else:
+            for j, (nr_reads_in_cl2, c_id2, seq2, reads_path) in enumerate(centers[i + 1:]):
+                if highest_aln_identity(seq, seq2) >= rc_identity_threshold:
+                    merged_nr_reads += nr_reads_in_cl2
+                    already_removed.add(c_id2)
+                    if type(reads_path) != list:
+                        all_reads.append(reads_path)
+                    else:
+                        for rp in reads_path:
+                            all_reads.append(rp)
+            filtered_centers.append([merged_nr_reads, c_id, seq, all_reads])
+    logging.debug("{0} consensus formed.".format(len(filtered_centers)))
+    return filtered_centers
+
+
+def form_draft_consensus(clusters, representatives, sorted_reads_fastq_file, work_dir, abundance_cutoff, args):
+    """Reference: modules/consensus.py:249-278 -> [[n_reads, c_id, consensus, reads_path], ...].
+    The per-cluster FASTQ files are written as in the reference; the drafts of all clusters are
+    computed in one batched launch."""
+    reads = {acc: (seq, qual) for acc, seq, qual in _read_fastq(sorted_reads_fastq_file)}
+    centers, todo = [], []
+    singletons, discarded = 0, []
+    for c_id, all_read_acc in sorted(clusters.items(), key=lambda x: (len(x[1]), representatives[x[0]][5]), reverse=True):
+        n = len(all_read_acc)
+        if n >= abundance_cutoff:
+            path = os.path.join(work_dir, "reads_c_id_{0}.fq".format(c_id))
+            used = []
+            with open(path, "w") as f:
+                for i, acc in enumerate(all_read_acc):
+                    if args.max_seqs_for_consensus >= 0 and i >= args.max_seqs_for_consensus:
+                        break
+                    seq, qual = reads[acc]
+                    f.write("@{0}\n{1}\n{2}\n{3}\n".format(acc, seq, "+", qual))
+                    used.append((seq, qual))
+            todo.append((n, c_id, path, used))
+        elif n == 1:
+            singletons += 1
+        elif n > 1:
+            discarded.append(n)
+    if todo:
+        eng = _engine.get_engine(getattr(args, "device", 0))
+        flat, lists = [], []
+        for _n, _c, _p, used in todo:
+            lists.append(list(range(len(flat), len(flat) + len(used))))
+            flat.extend(used)
+        eng.upload_records(flat)
+        cons, _nodes = draft_consensus_batch(eng, lists)
+        for (n, c_id, path, _u), c in zip(todo, cons):
+            with open(os.path.join(work_dir, "spoa_tmp.fa"), "w") as f:
+                f.write(">Consensus LN:i:{0}\n{1}\n".format(len(c), c))
+            centers.append([n, c_id, c, path])
+    logging.debug("{0} singletons were discarded".format(singletons))
+    logging.debug("{0} clusters were discarded due to not passing the abundance_cutoff: a total of {1} reads "
+                  "were discarded. Highest abundance among them: {2} reads.".format(len(discarded), sum(discarded), max(discarded or [0])))
+    return centers
+
+
+def polish_sequences(centers, args):
+    """Reference: modules/consensus.py:186-246 (racon branch; --medaka is not provided here)."""
+    if getattr(args, "medaka", False):
+        raise NotImplementedError("medaka polishing is outside this implementation (use --racon)")
+    for folder in glob.glob(os.path.join(args.outfolder, "racon_cl_id_*")):
+        shutil.rmtree(folder)
+    for file in glob.glob(os.path.join(args.outfolder, "consensus_reference_*")):
+        os.remove(file)
+    for i, (nr_reads_in_cluster, c_id, center, all_reads) in enumerate(centers):
+        spoa_center_file = os.path.join(args.outfolder, "consensus_reference_{0}.fasta".format(c_id))
+        with open(spoa_center_file, "w") as f:
+            f.write(">{0}\n{1}\n".format("consensus_cl_id_{0}_total_supporting_reads_{1}".format(c_id, nr_reads_in_cluster), center))
+        all_reads_file = os.path.join(args.outfolder, "reads_to_consensus_{0}.fastq".format(c_id))
+        with open(all_reads_file, "w") as f:
+            for fasta_file in all_reads:
+                reads = {acc: (seq, qual) for acc, seq, qual in _read_fastq(fasta_file)}
+                for acc, (seq, qual) in reads.items():
+                    f.write("@{0}\n{1}\n{2}\n{3}\n".format(acc.split()[0], seq, "+", qual))
+        if args.racon:
+            polishing_outfolder = os.path.join(args.outfolder, "racon_cl_id_{0}".format(c_id))
+            help_functions.mkdir_p(polishing_outfolder)
+            run_racon(all_reads_file, spoa_center_file, polishing_outfolder, "1", args.racon_iter)
+            with open(os.path.join(polishing_outfolder, "consensus.fasta"), "r") as cf:
+                centers[i][2] = cf.readlines()[1].strip()
+    return centers

@@ -132,7 +132,63 @@ def _oracle_align(lib, a, b, o, k, m):
     return c, sc.value
 
 
-def test_k4_block_align_random_pairs(eng):
+@pytest.mark.parametrize("payload_kernel", [0, 1])
+def test_k4_block_align_random_pairs(eng, payload_kernel):
+    eng.set_option(2, payload_kernel)      # 0: DP + trace + traceback kernels, 1: trace-free payload kernel
+    try:
+        _k4_random_pairs(eng)
+    finally:
+        eng.set_option(2, 0)
+
+
+def test_k4_paths_identity_and_windows(eng):
+    """Score, identity and window breaking points against the oracle's expanded CIGAR."""
+    from oracle import consensus_oracle as co
+    rng = np.random.default_rng(5)
+
+    def rnd(n):
+        return "".join(rng.choice(list("ACGT"), size=n))
+
+    def noisy(s, e):
+        out = []
+        for ch in s:
+            r = rng.random()
+            if r < e / 3:
+                continue
+            if r < 2 * e / 3:
+                out.append("ACGT"[rng.integers(4)])
+            out.append(ch if r >= e else "ACGT"[rng.integers(4)])
+        return "".join(out) or "A"
+
+    targets = [rnd(760), rnd(1203), rnd(499), rnd(500), rnd(501), rnd(30)]
+    reads, A, B = [], [], []
+    for ti, t in enumerate(targets):
+        for e in (0.0, 0.08, 0.2):
+            reads.append(noisy(t, e)); A.append(len(reads) - 1); B.append(-ti - 1)
+        reads.append(noisy(t[len(t) // 3:], 0.1)); A.append(len(reads) - 1); B.append(-ti - 1)
+        reads.append(rnd(200)); A.append(len(reads) - 1); B.append(-ti - 1)
+    eng.upload_records([(s, "5" * len(s)) for s in reads])
+    score, nmatch, ncols, win = eng.sg_align_paths(A, B, [3] * len(A), aux=targets, window=500, want_windows=True)
+    for i in range(len(A)):
+        t = targets[-B[i] - 1]
+        ops, sc = co.align_ops(reads[A[i]], t, open_pen=3)
+        assert int(score[i]) == sc
+        assert int(ncols[i]) == len(ops) and int(nmatch[i]) == ops.count("=")
+        exp = co.window_segments(ops, len(t), 500)
+        for w in range(16):
+            got = tuple(int(x) for x in win[i, w])
+            if w in exp:
+                assert got == exp[w], (i, w)
+            else:
+                assert got == (-1, -1, -1, -1), (i, w)
+    # both operands from the auxiliary arena (consensus vs consensus, consensus.py:129-145)
+    eng.upload_records([("ACGT", "5555")])
+    s2, m2, c2 = eng.sg_align_paths([-1, -1], [-2, -1], [3, 3], aux=[targets[0], noisy(targets[0], 0.05)])
+    ops, sc = co.align_ops(targets[0], targets[0])
+    assert int(s2[1]) == sc and int(m2[1]) == len(targets[0]) == int(c2[1])
+
+
+def _k4_random_pairs(eng):
     lib = oc._lib()
     rng = np.random.default_rng(11)
 
