@@ -344,6 +344,58 @@ def run_ours(args):
         if st["align_cells"] and phase["k4"] > 0:
             result["k4_gcups"] = st["align_cells"] * args.steps / (phase["k4"] / 1000.0) / 1e9
 
+
+    # ---- consensus leg (BASELINE.json configs[2] shape): draft POA + racon-style polish of every
+    # cluster above the abundance cut-off, capped with the reference's own --max_seqs_for_consensus
+    if rank == 0 and world == 1 and not args.no_consensus:
+        from ngspeciesid_b200.modules import consensus as C
+        assign = state["assign"]
+        rep = np.where(assign >= 0, assign, np.arange(n_mine))
+        cutoff = int(args.abundance_ratio * n_mine)
+        ids, counts = np.unique(rep, return_counts=True)
+        big = ids[counts >= cutoff]
+        order_idx = np.argsort(rep, kind="stable")
+        starts = np.searchsorted(rep[order_idx], big)
+        lists = [order_idx[st:st + c][: args.max_seqs].tolist() for st, c in zip(starts, counts[counts >= cutoff])]
+        lens_ = np.diff(s_off)
+        used_bases = int(sum(int(lens_[l].sum()) for l in lists))
+
+        def consensus_step():
+            drafts, _nodes = C.draft_consensus_batch(eng, lists)
+            return C.polish_batch(eng, drafts, lists, args.racon_iter)
+
+        l0 = eng.launch_count()
+        consensus_step()
+        eng.sync()
+        tc = time.perf_counter()
+        csteps = max(1, min(args.steps, 2))
+        for _ in range(csteps):
+            cons = consensus_step()
+        eng.sync()
+        dtc_ = (time.perf_counter() - tc) / csteps
+        result["consensus"] = {
+            "metric": "consensus bp/s (read bases consumed by draft POA + %d polish rounds / wall time)" % args.racon_iter,
+            "value": used_bases * (1 + args.racon_iter) / dtc_, "unit": "bp/s", "seconds_per_step": dtc_,
+            "clusters": len(lists), "reads_used": int(sum(len(l) for l in lists)),
+            "config": "clusters >= abundance_ratio %.3f x reads, --max_seqs_for_consensus %d, --racon_iter %d; host buffers in, "
+                      "consensus strings out" % (args.abundance_ratio, args.max_seqs, args.racon_iter),
+            "consensus_lengths": [len(c) for c in cons][:8], "gpu_launches": int(eng.launch_count() - l0)}
+        if not args.no_cpu and lists:
+            from oracle import consensus_oracle as co
+            sample = lists[0][: args.cpu_consensus_reads]
+            recs = [(seq[offsets[i]:offsets[i + 1]].tobytes().decode(), qual[offsets[i]:offsets[i + 1]].tobytes().decode()) for i in sample]
+            t3 = time.perf_counter()
+            d0 = co.spoa_consensus(recs)
+            p0 = co.racon_polish(d0, recs, args.racon_iter)
+            dt3 = time.perf_counter() - t3
+            sb = sum(len(r[0]) for r in recs)
+            g_d, _ = C.draft_consensus_batch(eng, [sample])
+            g_p = C.polish_batch(eng, g_d, [sample], args.racon_iter)[0]
+            result["consensus"]["cpu_baseline"] = {
+                "value": sb * (1 + args.racon_iter) / dt3, "unit": "bp/s", "cores": 1, "kind": "port",
+                "sample": "first %d reads of the largest cluster, oracle/poa_oracle.cpp + consensus_oracle.py" % len(sample)}
+            result["consensus"]["parity_sample_edit_distance"] = int(co.edit_distance(g_p, p0))
+
     # ---- K1 roofline on a replicated input far larger than L2 (rank 0 only)
     if rank == 0 and not args.no_roofline:
         rep = max(1, int(args.roofline_reads // max(1, n_mine)))
@@ -479,6 +531,11 @@ def main():
     ap.add_argument("--roofline-reads", dest="roofline_reads", type=int, default=2000000)
     ap.add_argument("--no-roofline", dest="no_roofline", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--no-consensus", dest="no_consensus", action="store_true")
+    ap.add_argument("--abundance-ratio", dest="abundance_ratio", type=float, default=0.02)
+    ap.add_argument("--max-seqs", dest="max_seqs", type=int, default=200, help="--max_seqs_for_consensus of the consensus leg")
+    ap.add_argument("--racon-iter", dest="racon_iter", type=int, default=3)
+    ap.add_argument("--cpu-consensus-reads", dest="cpu_consensus_reads", type=int, default=60)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -14,6 +14,7 @@
 #include "poa_core.cuh"
 
 #define K5_THREADS 256
+#define K5_MAXC 16                 // columns per thread: layers up to 4096 bases
 
 struct K5Args {
     int64_t n_jobs;
@@ -23,22 +24,31 @@ struct K5Args {
     const uint8_t *aux; const int64_t *aoff;
     int mode, m, x, g, trim;
     uint8_t *arena; size_t graph_bytes;
-    int Vcap, Ecap, Acap, Scap, Lmax;
+    int Vcap, Ecap, Acap, Scap, Lmax, ring_rows;
     int32_t *H; size_t h_words;
+    int4 *rmeta_all; uint32_t *rinfo_all;       // per slot: Vcap entries each
     uint8_t *out; int64_t out_stride; int32_t *out_len; int32_t *out_nodes; int32_t *err;
+    long long *cycles;          // optional: per job {dp, traceback, graph update + sort, consensus} clock64 sums
 };
 
+template <int CMAX>
 __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
 {
+    __shared__ int4 s_meta[K5_THREADS];
+    __shared__ uint32_t s_info[K5_THREADS];
     __shared__ PoaGraph G;
-    __shared__ int s_wmax[K5_THREADS / 32];
+    __shared__ int s_wmax[2][K5_THREADS / 32];
+    extern __shared__ __align__(16) int rowbuf[];        // ring of ring_rows DP rows of Lmax+2 ints
     __shared__ int s_best[K5_THREADS / 32][3];
     __shared__ int s_bi, s_bj, s_go;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     int32_t *H = A.H + (size_t)blockIdx.x * A.h_words;
+    int4 *rmeta = A.rmeta_all + (size_t)blockIdx.x * A.Vcap;
+    uint32_t *rinfo = A.rinfo_all + (size_t)blockIdx.x * A.Vcap;
 
     for (int64_t job = blockIdx.x; job < A.n_jobs; job += gridDim.x) {
         if (tid == 0) poa_graph_bind(G, A.arena + (size_t)blockIdx.x * A.graph_bytes, A.Vcap, A.Ecap, A.Acap, A.Scap, A.Lmax);
+        long long cyc_dp = 0, cyc_tb = 0, cyc_add = 0, cyc_cons = 0, t0 = 0;
         __syncthreads();
         for (int64_t li = A.job_off[job]; li < A.job_off[job + 1]; ++li) {
             const int src = A.layer_src[li], lb = A.layer_begin[li], L = A.layer_len[li];
@@ -52,57 +62,143 @@ __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
             }
             const size_t ld = (size_t)L + 1;
             const int g = A.g;
-            for (int j = tid; j <= L; j += K5_THREADS) H[j] = A.mode ? j * g : 0;
-            const int C = (L + K5_THREADS - 1) / K5_THREADS;
+            if (tid == 0) t0 = clock64();
+            // ---- per-row metadata (letter + up to 4 predecessor rows), built in parallel
+            for (int r = tid; r < V; r += K5_THREADS) {
+                const int v = G.order[r];
+                int4 pm = make_int4(-1, -1, -1, -1);
+                int np = 0;
+                for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e], ++np) {
+                    const int pr = G.rank[G.e_from[e]] + 1;
+                    if (np == 0) pm.x = pr; else if (np == 1) pm.y = pr; else if (np == 2) pm.z = pr; else if (np == 3) pm.w = pr;
+                }
+                if (np == 0) pm.x = 0;                      // source node: virtual row 0
+                rmeta[r] = pm;
+                rinfo[r] = ((uint32_t)np << 8) | G.letter[v];
+            }
+            for (int j = tid; j <= L; j += K5_THREADS) { const int h = A.mode ? j * g : 0; __stcg(&H[j], h); rowbuf[j] = h; }
+            const int C = (L + K5_THREADS - 1) / K5_THREADS;          // <= CMAX by construction
             const int j0 = 1 + tid * C, j1 = min(L, j0 + C - 1);
             int bestv = 0, besti = 0, bestj = 0;
             __syncthreads();
-            for (int r = 0; r < V; ++r) {
-                const int v = G.order[r];
-                const uint8_t c = G.letter[v];
-                const size_t row = (size_t)(r + 1) * ld;
-                const int eh = G.in_head[v];
-                // column 0
-                int h0 = 0;
-                if (A.mode) {
-                    int p = POA_NEG;
-                    if (eh < 0) p = 0;
-                    for (int e = eh; e >= 0; e = G.e_next_in[e]) p = max(p, H[(size_t)(G.rank[G.e_from[e]] + 1) * ld]);
-                    h0 = p + g;
-                }
-                // A[j] - g*j over this thread's chunk, running prefix maximum
-                int run = (tid == 0) ? h0 : POA_NEG;
-                for (int j = j0; j <= j1; ++j) {
-                    const int sc = (c == s[j - 1]) ? A.m : A.x;
-                    int h = POA_NEG;
-                    if (eh < 0) h = max(H[j - 1] + sc, H[j] + g);
-                    for (int e = eh; e >= 0; e = G.e_next_in[e]) {
-                        const size_t pr = (size_t)(G.rank[G.e_from[e]] + 1) * ld;
-                        h = max(h, max(H[pr + j - 1] + sc, H[pr + j] + g));
-                    }
-                    if (!A.mode) h = max(h, 0);
-                    run = max(run, h - g * j);
-                    H[row + j] = run;                      // provisional: chunk-local prefix maximum
-                }
-                // exclusive prefix maximum of the chunk maxima across the block
-                int incl = run;
+            // ring of the most recent DP rows in shared memory: matrix row q lives in slot q % R
+            const int R = A.ring_rows, rstride = A.Lmax + 2;
+            uint8_t sreg[CMAX];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int o = __shfl_up_sync(NGSID_FULL_MASK, incl, d);
-                    if (lane >= d) incl = max(incl, o);
-                }
-                if (lane == 31) s_wmax[wid] = incl;
+            for (int t = 0; t < CMAX; ++t) sreg[t] = (j0 + t <= j1) ? s[j0 + t - 1] : 0;
+            for (int rb = 0; rb < V; rb += K5_THREADS) {
                 __syncthreads();
-                int carry = __shfl_up_sync(NGSID_FULL_MASK, incl, 1);
-                if (lane == 0) carry = POA_NEG;
-                for (int w = 0; w < wid; ++w) carry = max(carry, s_wmax[w]);
-                for (int j = j0; j <= j1; ++j) {
-                    const int hv = max(H[row + j], carry) + g * j;
-                    H[row + j] = hv;
-                    if (!A.mode && hv > bestv) { bestv = hv; besti = r + 1; bestj = j; }
-                }
-                if (tid == 0) H[row] = h0;
+                if (rb + tid < V) { s_meta[tid] = rmeta[rb + tid]; s_info[tid] = rinfo[rb + tid]; }
                 __syncthreads();
+                const int rend = min(V, rb + K5_THREADS);
+                for (int r = rb; r < rend; ++r) {
+                    const int4 pm = s_meta[r - rb];
+                    const uint32_t info = s_info[r - rb];
+                    const uint8_t c = (uint8_t)(info & 255u);
+                    const int np = (int)(info >> 8);
+                    const int mrow = r + 1;
+                    const size_t row = (size_t)mrow * ld;
+                    int *curb = rowbuf + (size_t)(mrow % R) * rstride;
+                    int h0 = 0;
+                    int run, val[CMAX];
+                    if (np <= 4) {
+                        const int prs[4] = {pm.x, pm.y, pm.z, pm.w};
+                        // gather: every predecessor value first (ring or L2), then the maxima
+                        int pa[4][CMAX + 1];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int pr = prs[u];
+                            if (pr >= 0) {
+                                if (mrow - pr < R) {
+                                    const int *pb = rowbuf + (size_t)(pr % R) * rstride;
+#pragma unroll
+                                    for (int t = 0; t <= CMAX; ++t) pa[u][t] = (j0 + t - 1 <= j1) ? pb[j0 + t - 1] : POA_NEG;
+                                    if (A.mode && tid == 0) h0 = (u == 0) ? pb[0] : max(h0, pb[0]);
+                                } else {
+                                    const int32_t *hp = H + (size_t)pr * ld;
+#pragma unroll
+                                    for (int t = 0; t <= CMAX; ++t) pa[u][t] = (j0 + t - 1 <= j1) ? __ldcg(hp + j0 + t - 1) : POA_NEG;
+                                    if (A.mode && tid == 0) { const int z = __ldcg(hp); h0 = (u == 0) ? z : max(h0, z); }
+                                }
+                            } else {
+#pragma unroll
+                                for (int t = 0; t <= CMAX; ++t) pa[u][t] = POA_NEG;
+                            }
+                        }
+                        if (A.mode) h0 += g;
+                        run = (tid == 0) ? h0 : POA_NEG;
+#pragma unroll
+                        for (int t = 0; t < CMAX; ++t) {
+                            const int j = j0 + t;
+                            val[t] = POA_NEG;
+                            if (j <= j1) {
+                                const int sc = (c == sreg[t]) ? A.m : A.x;
+                                int dg = max(max(pa[0][t], pa[1][t]), max(pa[2][t], pa[3][t]));
+                                int up = max(max(pa[0][t + 1], pa[1][t + 1]), max(pa[2][t + 1], pa[3][t + 1]));
+                                int h = max(dg + sc, up + g);
+                                if (!A.mode) h = max(h, 0);
+                                run = max(run, h - g * j);
+                                val[t] = run;
+                            }
+                        }
+                    } else {
+                        const int v = G.order[r];
+                        if (A.mode) {
+                            int p = POA_NEG;
+                            for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) p = max(p, __ldcg(&H[(size_t)(G.rank[G.e_from[e]] + 1) * ld]));
+                            h0 = p + g;
+                        }
+                        run = (tid == 0) ? h0 : POA_NEG;
+#pragma unroll
+                        for (int t = 0; t < CMAX; ++t) {
+                            const int j = j0 + t;
+                            val[t] = POA_NEG;
+                            if (j <= j1) {
+                                const int sc = (c == sreg[t]) ? A.m : A.x;
+                                int h = POA_NEG;
+                                for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) {
+                                    const int32_t *hp = H + (size_t)(G.rank[G.e_from[e]] + 1) * ld + j;
+                                    h = max(h, max(__ldcg(hp - 1) + sc, __ldcg(hp) + g));
+                                }
+                                if (!A.mode) h = max(h, 0);
+                                run = max(run, h - g * j);
+                                val[t] = run;
+                            }
+                        }
+                    }
+                    int incl = run;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        int o = __shfl_up_sync(NGSID_FULL_MASK, incl, d);
+                        if (lane >= d) incl = max(incl, o);
+                    }
+                    if (lane == 31) s_wmax[r & 1][wid] = incl;
+                    __syncthreads();
+                    int carry = __shfl_up_sync(NGSID_FULL_MASK, incl, 1);
+                    if (lane == 0) carry = POA_NEG;
+                    {
+                        int wt = (lane < K5_THREADS / 32) ? s_wmax[r & 1][lane] : POA_NEG;
+#pragma unroll
+                        for (int d = 1; d < K5_THREADS / 32; d <<= 1) {
+                            int o = __shfl_up_sync(NGSID_FULL_MASK, wt, d);
+                            if (lane >= d) wt = max(wt, o);
+                        }
+                        int prevw = __shfl_sync(NGSID_FULL_MASK, wt, max(wid - 1, 0));
+                        if (wid > 0) carry = max(carry, prevw);
+                    }
+#pragma unroll
+                    for (int t = 0; t < CMAX; ++t) {
+                        const int j = j0 + t;
+                        if (j <= j1) {
+                            const int hv = max(val[t], carry) + g * j;
+                            curb[j] = hv;
+                            __stcg(&H[row + j], hv);
+                            if (!A.mode && hv > bestv) { bestv = hv; besti = r + 1; bestj = j; }
+                        }
+                    }
+                    if (tid == 0) { curb[0] = h0; __stcg(&H[row], h0); }
+                    __syncthreads();
+                }
             }
             // ---- end cell
             if (!A.mode) {
@@ -117,6 +213,8 @@ __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
                 __syncthreads();
             }
             if (tid == 0) {
+                long long t1 = clock64();
+                cyc_dp += t1 - t0;
                 int bv, bi = 0, bj = 0;
                 if (!A.mode) {
                     bv = 0;
@@ -129,14 +227,17 @@ __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
                     for (int r = 0; r < V; ++r) {
                         const int v = G.order[r];
                         if (G.out_head[v] < 0) {
-                            const int hv = H[(size_t)(r + 1) * ld + L];
+                            const int hv = __ldcg(&H[(size_t)(r + 1) * ld + L]);
                             if (hv > bv) { bv = hv; bi = r + 1; bj = L; }
                         }
                     }
                 }
                 int n_aln = 0;
                 if (!(A.mode == 0 && bv == 0)) n_aln = poa_traceback(G, H, ld, s, A.mode, A.m, A.x, g, bi, bj);
+                long long t2 = clock64();
+                cyc_tb += t2 - t1;
                 poa_add_alignment(G, n_aln, s, q, L);
+                cyc_add += clock64() - t2;
                 s_go = (G.err == 0 && G.V + A.Lmax + 2 < G.Vcap) ? 1 : 0;
                 if (!s_go && G.err == 0) G.err = 1;
             }
@@ -145,7 +246,10 @@ __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
         }
         if (tid == 0) {
             int len = -1;
+            long long t3 = clock64();
             if (G.err == 0) len = poa_consensus(G, A.trim, A.out + (size_t)job * A.out_stride, (int)A.out_stride);
+            cyc_cons = clock64() - t3;
+            if (A.cycles) { A.cycles[job * 4] = cyc_dp; A.cycles[job * 4 + 1] = cyc_tb; A.cycles[job * 4 + 2] = cyc_add; A.cycles[job * 4 + 3] = cyc_cons; }
             A.out_len[job] = len;
             if (A.out_nodes) A.out_nodes[job] = G.V;
             if (G.err) atomicMax(A.err, G.err);

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include "ngsid_internal.cuh"
 #include "k1_minimizers.cuh"
 #include "k2_map.cuh"
@@ -68,7 +69,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
                       &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
-                      &ctx->d_newslots, &ctx->d_poa_arena, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+                      &ctx->d_newslots, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
     cudaEventDestroy(ctx->ev0);
@@ -524,6 +525,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         if (layer_begin[l] < 0 || layer_len[l] < 0 || (int64_t)layer_begin[l] + layer_len[l] > len) return fail(ctx, NGSID_EINVAL, "layer range out of bounds");
         Lmax = std::max(Lmax, (int)layer_len[l]);
     }
+    if (Lmax > K5_MAXC * K5_THREADS) return fail(ctx, NGSID_EUNSUPPORTED, "POA layer longer than 4096 bases");
     int rc = upload_aux(ctx, aux_seq, aux_off, n_aux);
     if (rc) return rc;
     const int Vcap = params->max_nodes > 0 ? std::max(params->max_nodes, Lmax + 16) : std::max(4096, 32 * Lmax);
@@ -535,6 +537,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     while (slots > 1 && (double)slots * (double)(h_words * 4 + gbytes) > 48e9) slots /= 2;
     CUDA_TRY(ctx, ctx->d_poa_arena.ensure(gbytes * slots));
     CUDA_TRY(ctx, ctx->d_poa_h.ensure(h_words * 4 * slots));
+    CUDA_TRY(ctx, ctx->d_poa_meta.ensure((size_t)Vcap * 20 * slots + 64));
     CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)n_jobs * out_stride));
     CUDA_TRY(ctx, ctx->d_poa_len.ensure((size_t)n_jobs * 4));
     CUDA_TRY(ctx, ctx->d_poa_nodes.ensure((size_t)n_jobs * 4));
@@ -557,9 +560,29 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     A.arena = ctx->d_poa_arena.as<uint8_t>(); A.graph_bytes = gbytes;
     A.Vcap = Vcap; A.Ecap = Ecap; A.Acap = Acap; A.Scap = Scap; A.Lmax = Lmax;
     A.H = ctx->d_poa_h.as<int32_t>(); A.h_words = h_words;
+    A.rmeta_all = ctx->d_poa_meta.as<int4>();
+    A.rinfo_all = reinterpret_cast<uint32_t *>(ctx->d_poa_meta.as<uint8_t>() + (size_t)Vcap * 16 * slots);
     A.out = ctx->d_poa_out.as<uint8_t>(); A.out_stride = out_stride; A.out_len = ctx->d_poa_len.as<int32_t>();
     A.out_nodes = ctx->d_poa_nodes.as<int32_t>(); A.err = ctx->d_poa_err.as<int32_t>();
-    k5_poa_kernel<<<slots, K5_THREADS, 0, ctx->stream>>>(A);
+    A.cycles = nullptr;
+    if (getenv("NGSID_POA_CYCLES")) {
+        CUDA_TRY(ctx, ctx->d_win.ensure((size_t)n_jobs * 32));
+        A.cycles = ctx->d_win.as<long long>();
+    }
+    const int ring_rows = (int)std::max<size_t>(2, std::min<size_t>(64, (size_t)(160 * 1024) / ((size_t)(Lmax + 2) * sizeof(int))));
+    A.ring_rows = ring_rows;
+    const size_t k5_smem = (size_t)ring_rows * (Lmax + 2) * sizeof(int);
+    const int cneed = (Lmax + K5_THREADS - 1) / K5_THREADS;
+#define K5_LAUNCH(CM)                                                                                        \
+    do {                                                                                                     \
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k5_poa_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5_smem)); \
+        k5_poa_kernel<CM><<<slots, K5_THREADS, k5_smem, ctx->stream>>>(A);                                   \
+    } while (0)
+    if (cneed <= 2) K5_LAUNCH(2);
+    else if (cneed <= 4) K5_LAUNCH(4);
+    else if (cneed <= 8) K5_LAUNCH(8);
+    else K5_LAUNCH(16);
+#undef K5_LAUNCH
     KERNEL_CHECK(ctx);
     int err = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -567,6 +590,14 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     CUDA_TRY(ctx, cudaMemcpyAsync(out_len, ctx->d_poa_len.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_nodes) CUDA_TRY(ctx, cudaMemcpyAsync(out_nodes, ctx->d_poa_nodes.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (A.cycles) {
+        std::vector<long long> cyc((size_t)n_jobs * 4);
+        cudaMemcpy(cyc.data(), A.cycles, cyc.size() * 8, cudaMemcpyDeviceToHost);
+        long long tot[4] = {0, 0, 0, 0};
+        for (int64_t j = 0; j < n_jobs; ++j) for (int q = 0; q < 4; ++q) tot[q] += cyc[j * 4 + q];
+        fprintf(stderr, "[k5] jobs %lld layers %lld: cycles dp %.3g traceback %.3g update+sort %.3g consensus %.3g\n",
+                (long long)n_jobs, (long long)n_layers, (double)tot[0], (double)tot[1], (double)tot[2], (double)tot[3]);
+    }
     if (err) {
         char msg[160];
         snprintf(msg, sizeof msg, "POA graph capacity exceeded (code %d, max_nodes %d): raise max_nodes or cap the reads per consensus", err, Vcap);

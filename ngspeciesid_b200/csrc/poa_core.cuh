@@ -15,6 +15,13 @@
 
 #define POA_NEG (-(1 << 28))
 
+// DP matrix reads: the kernel writes the matrix with L1-bypassing stores, so reads bypass L1 too
+#if defined(__CUDA_ARCH__)
+#define POA_LDH(p) __ldcg(p)
+#else
+#define POA_LDH(p) (*(p))
+#endif
+
 struct PoaGraph {
     int32_t Vcap, Ecap, Acap, Scap;
     int32_t V, E, A, n_seqs, err;           // err: 1 node, 2 edge, 3 aligned-list, 4 stack overflow
@@ -169,7 +176,7 @@ POA_HD int poa_traceback(PoaGraph &G, const int32_t *H, size_t ld, const uint8_t
                          int m, int x, int g, int bi, int bj)
 {
     int i = bi, j = bj, n = 0;
-#define POA_AT(r, c) H[(size_t)(r) * ld + (size_t)(c)]
+#define POA_AT(r, c) POA_LDH(&H[(size_t)(r) * ld + (size_t)(c)])
     while ((mode == 0) ? (POA_AT(i, j) != 0) : (i != 0 || j != 0)) {
         const int h = POA_AT(i, j);
         bool done = false;
