@@ -184,28 +184,38 @@ k1_minimizers_kernel(const uint32_t *__restrict__ packed, const int64_t *__restr
 //     slot, key = code << 4 | slot-in-block, and the sliding minimum over 8 k-mers is
 //     min(suffix minimum of the previous block, prefix minimum of this block) (van Herk /
 //     Gil-Werman), branch-free, leftmost on ties because the slot index sits in the low key bits;
-//   * a minimizer is written whenever the argmin slot of consecutive windows changes.
+//   * a minimizer is recorded whenever the window minimum changes; records go to a per-thread
+//     ring in shared memory and leave for HBM in rows of 16 records = 128 bytes, written by half a
+//     warp at a time (fully coalesced), so DRAM sees whole lines instead of scattered 8-byte stores;
+//   * the loop is block-centric and warp-uniform: every iteration each lane refills its FIFO
+//     (cheap, variable) and runs exactly one block step (expensive, always useful).
 // Reads whose compressed length is < w (reference quirk, one truncated-window minimizer) are
 // appended to `slow_list` and finished by k1_minimizers_kernel.
 #define K1F_INF 0xffffffffu
+#define K1F_THREADS 128
+#define K1F_RING 32                 // records per thread ring
+#define K1F_RSTRIDE 33              // ring stride in records (padding against bank conflicts)
+#define K1F_ROW 16                  // records per flushed row (128 bytes)
 
 struct K1FastState {
     uint32_t suf[9];
     uint32_t code;
     int base;          // slot index of the first slot of the next block
-    int last_slot;
+    uint32_t last_key; // key of the last recorded minimizer in the frame of the current block
     uint32_t n_out;
 };
 
+// One block of 8 compressed bases. Records (key, block base) pairs into the thread's ring.
 template <bool PARTIAL>
 __device__ __forceinline__ void k1_fast_block(K1FastState &S, uint32_t ch, int nvalid, int k, int w,
-                                              uint32_t kmask, Minimizer *__restrict__ out)
+                                              uint32_t kmask, uint2 *__restrict__ ring)
 {
     uint32_t key[8];
     uint32_t pm = K1F_INF;
+    const bool warm = S.base + 7 < w - 1;          // no complete window ends in this block
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
-        uint32_t b = (ch >> (14 - 2 * t)) & 3u;
+        const uint32_t b = (ch >> (14 - 2 * t)) & 3u;
         S.code = ((S.code << 2) | b) & kmask;
         const int slot = S.base + t;
         uint32_t kk = (S.code << 4) | (uint32_t)(8 + t);
@@ -214,13 +224,12 @@ __device__ __forceinline__ void k1_fast_block(K1FastState &S, uint32_t ch, int n
         key[t] = kk;
         pm = min(pm, kk);
         const uint32_t m = min(S.suf[t + 1], pm);
-        const int mslot = S.base - 8 + (int)(m & 15u);
-        bool emit = (slot >= w - 1) && (mslot != S.last_slot);
+        bool emit = (m != S.last_key) && !warm && (slot >= w - 1);
         if (PARTIAL) emit = emit && (t < nvalid);
         if (emit) {
-            out[S.n_out] = make_uint2(m >> 4, (uint32_t)(mslot - (k - 1)));
+            ring[S.n_out & (K1F_RING - 1)] = make_uint2(m, (uint32_t)S.base);
             S.n_out++;
-            S.last_slot = mslot;
+            S.last_key = m;
         }
     }
     uint32_t sm = K1F_INF;
@@ -229,10 +238,20 @@ __device__ __forceinline__ void k1_fast_block(K1FastState &S, uint32_t ch, int n
         sm = min(sm, key[t]);
         S.suf[t] = sm - 8u;          // becomes "previous block": slot tags 0..7
     }
+    // the same record seen from the next block's frame; a record from the previous block can no
+    // longer be a window minimum, so it must not compare equal to anything
+    S.last_key = (S.last_key & 8u) ? S.last_key - 8u : (K1F_INF - 1u);
     S.base += 8;
 }
 
-__global__ void __launch_bounds__(128)
+// decode a ring record: key = code << 4 | tag, tag 0..7 = previous block, 8..15 = block at `base`
+__device__ __forceinline__ Minimizer k1_fast_decode(uint2 rec, int k)
+{
+    const int slot = (int)rec.y - 8 + (int)(rec.x & 15u);
+    return make_uint2(rec.x >> 4, (uint32_t)(slot - (k - 1)));
+}
+
+__global__ void __launch_bounds__(K1F_THREADS)
 k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ woff,
                const int64_t *__restrict__ off, const int64_t *__restrict__ moff,
                Minimizer *__restrict__ mins, uint32_t *__restrict__ nmin,
@@ -240,6 +259,7 @@ k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ 
                int32_t *__restrict__ slow_list, int32_t *__restrict__ slow_n)
 {
     __shared__ uint16_t lut[1024];
+    __shared__ uint2 rings[K1F_THREADS * K1F_RSTRIDE];
     for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) {
         uint32_t prev = idx >> 8, byte = idx & 255, bits = 0, cnt = 0;
 #pragma unroll
@@ -251,70 +271,110 @@ k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ 
         lut[idx] = (uint16_t)((cnt << 8) | bits);
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31;
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const int L = (int)(off[r + 1] - off[r]);
-    const uint4 *pk = reinterpret_cast<const uint4 *>(packed + woff[r]);
-    Minimizer *out = mins + moff[r];
+    const bool have = r < n_reads;
+    const int L = have ? (int)(off[r + 1] - off[r]) : 0;
+    const uint2 *pk = reinterpret_cast<const uint2 *>(packed + (have ? woff[r] : 0));
+    Minimizer *out = mins + (have ? moff[r] : 0);
+    uint2 *ring = rings + threadIdx.x * K1F_RSTRIDE;
     const uint32_t kmask = (1u << (2 * k)) - 1u;
 
     K1FastState S;
 #pragma unroll
     for (int t = 0; t < 9; ++t) S.suf[t] = K1F_INF;
-    S.code = 0; S.base = 0; S.last_slot = -1; S.n_out = 0;
-    unsigned long long fifo = 0;
-    int avail = 0;
-    uint32_t prev = 0;
-    const int nwords_full = L >> 4;
-    const int nquads = (L + 63) >> 6;
-    uint4 cur = (nquads > 0) ? __ldg(pk) : make_uint4(0, 0, 0, 0);
-    if (L > 0) prev = (cur.x >> 30) ^ 1u;             // anything different from the first base
-    for (int qd = 0; qd < nquads; ++qd) {
-        uint4 nxt = (qd + 1 < nquads) ? __ldg(pk + qd + 1) : make_uint4(0, 0, 0, 0);
-        uint32_t words[4] = {cur.x, cur.y, cur.z, cur.w};
-#pragma unroll
-        for (int wq = 0; wq < 4; ++wq) {
-            const int wi = qd * 4 + wq;
-            uint32_t word = words[wq];
-            if (wi < nwords_full) {
-#pragma unroll
-                for (int bq = 0; bq < 4; ++bq) {
-                    uint32_t byte = word >> 24;
-                    word <<= 8;
-                    uint32_t e = lut[(prev << 8) | byte];
-                    uint32_t c = e >> 8;
-                    fifo = (fifo << (2 * c)) | (unsigned long long)(e & 255u);
-                    avail += (int)c;
-                    prev = byte & 3u;
+    S.code = 0; S.base = 0; S.last_key = K1F_INF - 1u; S.n_out = 0;
+    unsigned long long fifo = 0, inbuf = 0;
+    int avail = 0, inleft = 0;                  // bytes left in inbuf
+    int bytes_left = L >> 2;                    // whole bytes (4 bases) of input still to consume
+    int next_pair = 0;                          // next uint2 (8 bytes = 32 bases) to load
+    uint32_t prev = 0, n_fl = 0;
+    bool first = true, tail_done = (L == 0);
+    bool active = have;
+
+    while (__any_sync(NGSID_FULL_MASK, active)) {
+        if (active) {
+            // ---- refill the FIFO up to >= 8 kept bases
+            while (avail < 8 && bytes_left > 0) {
+                if (inleft == 0) {
+                    const uint2 v = __ldg(pk + next_pair++);
+                    inbuf = ((unsigned long long)v.x << 32) | v.y;
+                    inleft = 8;
+                    if (first) { prev = (v.x >> 30) ^ 1u; first = false; }
                 }
-            } else if (wi == nwords_full) {
-                const int rem = L & 15;
-                for (int t = 0; t < rem; ++t) {
-                    uint32_t b = word >> 30;
-                    word <<= 2;
-                    if (b != prev) { fifo = (fifo << 2) | b; avail++; }
-                    prev = b;
-                }
+                const uint32_t byte = (uint32_t)(inbuf >> 56);
+                inbuf <<= 8; --inleft; --bytes_left;
+                const uint32_t e = lut[(prev << 8) | byte];
+                const uint32_t c = e >> 8;
+                fifo = (fifo << (2 * c)) | (unsigned long long)(e & 255u);
+                avail += (int)c;
+                prev = byte & 3u;
             }
-            while (avail >= 8) {
-                uint32_t ch = (uint32_t)(fifo >> (2 * (avail - 8))) & 0xffffu;
+            if (avail < 8 && !tail_done) {
+                // the last 0..3 bases of the read sit in the next byte
+                const int rem = L & 3;
+                if (rem) {
+                    if (inleft == 0) {
+                        const uint2 v = __ldg(pk + next_pair++);
+                        inbuf = ((unsigned long long)v.x << 32) | v.y;
+                        inleft = 8;
+                        if (first) { prev = (v.x >> 30) ^ 1u; first = false; }
+                    }
+                    uint32_t byte = (uint32_t)(inbuf >> 56);
+                    for (int t = 0; t < rem; ++t) {
+                        const uint32_t b = (byte >> 6) & 3u;
+                        byte <<= 2;
+                        if (b != prev) { fifo = (fifo << 2) | b; avail++; }
+                        prev = b;
+                    }
+                }
+                tail_done = true;
+            }
+            if (avail >= 8) {
+                const uint32_t ch = (uint32_t)(fifo >> (2 * (avail - 8))) & 0xffffu;
                 avail -= 8;
-                k1_fast_block<false>(S, ch, 8, k, w, kmask, out);
+                k1_fast_block<false>(S, ch, 8, k, w, kmask, ring);
+            } else {
+                // input exhausted: last partial block, then this lane is done
+                if (avail > 0) {
+                    const uint32_t ch = (uint32_t)(fifo << (2 * (8 - avail))) & 0xffffu;
+                    const int nv = avail;
+                    avail = 0;
+                    k1_fast_block<true>(S, ch, nv, k, w, kmask, ring);
+                    S.base += nv - 8;            // base now equals the compressed length
+                }
+                active = false;
             }
         }
-        cur = nxt;
+        // ---- flush full rows of 16 records, two rows per round (16 lanes x 8 bytes each)
+        uint32_t fm = __ballot_sync(NGSID_FULL_MASK, have && (S.n_out - n_fl) >= K1F_ROW);
+        while (fm) {
+            const int l0 = __ffs(fm) - 1;
+            fm &= fm - 1;
+            int l1 = -1;
+            if (fm) { l1 = __ffs(fm) - 1; fm &= fm - 1; }
+            const int leader = (lane < 16) ? l0 : l1;
+            const int src = leader >= 0 ? leader : 0;
+            const uint32_t fl = __shfl_sync(NGSID_FULL_MASK, n_fl, src);
+            const unsigned long long op = __shfl_sync(NGSID_FULL_MASK, (unsigned long long)out, src);
+            if (leader >= 0) {
+                const int e = lane & 15;
+                const uint2 rec = rings[(threadIdx.x - lane + leader) * K1F_RSTRIDE + ((fl + e) & (K1F_RING - 1))];
+                reinterpret_cast<Minimizer *>(op)[fl + e] = k1_fast_decode(rec, k);
+            }
+            if (lane == l0 || lane == l1) n_fl += K1F_ROW;
+        }
     }
-    const int Lc = S.base + avail;
-    if (avail > 0) {
-        uint32_t ch = (uint32_t)(fifo << (2 * (8 - avail))) & 0xffffu;
-        k1_fast_block<true>(S, ch, avail, k, w, kmask, out);
-    }
+    if (!have) return;
+    const int Lc = S.base;
     if (Lc < w) {
         // compressed read shorter than w (or than k): the generic kernel reproduces the quirk
         int i = atomicAdd(slow_n, 1);
         slow_list[i] = (int32_t)r;
         return;
     }
+    // leftover records (< 16): written by the owning thread
+    for (uint32_t i = n_fl; i < S.n_out; ++i) out[i] = k1_fast_decode(ring[i & (K1F_RING - 1)], k);
     nmin[r] = S.n_out;
     lenc[r] = (uint32_t)Lc;
 }

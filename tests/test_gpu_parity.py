@@ -303,3 +303,66 @@ def test_clustering_matches_oracle_with_many_representatives(eng, p_table, seed,
     how = {"new": 0, "map": 1, "align": 2}
     assert list(via) == [how[h] for _r, _w, h in stats.trace]
     assert st["n_new_reps"] == sum(1 for x in exp if x < 0) > 100
+
+
+def test_clustering_properties_at_scale(eng, p_table):
+    """Size-independent properties on a set too large for the oracle to finish quickly: the result
+    does not depend on the speculation tile size, representatives are never assigned, every read
+    points at a representative, a second run is identical, and the first reads agree with the
+    oracle (the greedy pass on a prefix is the prefix of the greedy pass)."""
+    import bench
+    from ngspeciesid_b200 import engine as E
+    seq, qual, off, acc = bench.make_workload(20000, 4242, cache=False)
+    p_emp = oc.load_p_emp(p_table, 13, 20)
+    mg = E.max_gap_table(p_emp, 0.1)
+    eng.upload(seq, qual, off)
+    eng.minimizers(13, 20)
+    eng.quality_stats()
+    ranks = E.accession_ranks(acc)
+    order = np.arange(len(acc))
+    a1, v1, st1 = eng.cluster(13, 20, mg, order, ranks, tile_reads=0)
+    a2, v2, st2 = eng.cluster(13, 20, mg, order, ranks, tile_reads=1024)
+    a3, v3, _ = eng.cluster(13, 20, mg, order, ranks, tile_reads=0)
+    assert (a1 == a2).all() and (v1 == v2).all() and (a1 == a3).all()
+    reps = np.nonzero(a1 == -1)[0]
+    assert len(reps) >= 20 and st1["n_new_reps"] == len(reps)
+    assigned = a1[a1 >= 0]
+    assert np.isin(assigned, reps).all()                      # no chains: targets are representatives
+    assert (assigned < np.nonzero(a1 >= 0)[0]).all()          # a read joins an earlier read
+    assert st1["n_mapped"] + st1["n_aln_passed"] + len(reps) == len(acc)
+    n0 = 1200
+    ra = bench.read_array(seq, qual, off, acc, 0, n0)
+    stats = oc.Stats()
+    oc.single_clustering(ra, p_emp, oc.default_args(), stats)
+    assert [w for _r, w, _h in stats.trace] == list(a1[:n0])
+
+
+def test_k1_properties_at_scale(eng):
+    """Minimizer invariants on 50k reads: positions strictly increase, consecutive positions are at
+    most W apart, every k-mer code is the code at its position, window coverage is complete."""
+    import bench
+    seq, qual, off, acc = bench.make_workload(50000, 99, cache=False)
+    eng.upload(seq, qual, off)
+    k, w = 13, 20
+    eng.minimizers(k, w)
+    len_c, counts, kmer, pos = eng.get_minimizers()
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    assert (counts > 0).all()
+    d = np.diff(pos.astype(np.int64))
+    boundary = np.zeros(len(pos), dtype=bool)
+    boundary[starts[1:-1]] = True
+    inner = ~boundary[1:]
+    assert (d[inner] > 0).all() and (d[inner] <= w - k + 1).all()
+    first = pos[starts[:-1]]
+    last = pos[starts[1:] - 1]
+    assert (first <= w - k).all()
+    assert (last.astype(np.int64) >= len_c.astype(np.int64) - w).all()
+    # spot check codes against the oracle on a sample of reads
+    from ngspeciesid_b200.engine import decode_kmer
+    rng = np.random.default_rng(1)
+    for i in rng.integers(0, len(acc), size=40):
+        s = seq[off[i]:off[i + 1]].tobytes().decode()
+        sc, _ = oc.hpol_compress(s)
+        exp = oc.minimizers(sc, k, w)
+        got = [(decode_kmer(kmer[j], k), int(pos[j])) for j in range(starts[i], starts[i + 1])]
+        assert got == exp
