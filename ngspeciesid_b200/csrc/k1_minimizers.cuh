@@ -185,17 +185,17 @@ k1_minimizers_kernel(const uint32_t *__restrict__ packed, const int64_t *__restr
 //     min(suffix minimum of the previous block, prefix minimum of this block) (van Herk /
 //     Gil-Werman), branch-free, leftmost on ties because the slot index sits in the low key bits;
 //   * a minimizer is recorded whenever the window minimum changes; records go to a per-thread
-//     ring in shared memory and leave for HBM in rows of 16 records = 128 bytes, written by half a
-//     warp at a time (fully coalesced), so DRAM sees whole lines instead of scattered 8-byte stores;
+//     ring in shared memory and leave for HBM in rows of 8 records = 64 bytes (two full sectors),
+//     eight rows per warp-wide store, so DRAM sees whole sectors instead of scattered 8-byte stores;
 //   * the loop is block-centric and warp-uniform: every iteration each lane refills its FIFO
 //     (cheap, variable) and runs exactly one block step (expensive, always useful).
 // Reads whose compressed length is < w (reference quirk, one truncated-window minimizer) are
 // appended to `slow_list` and finished by k1_minimizers_kernel.
 #define K1F_INF 0xffffffffu
 #define K1F_THREADS 128
-#define K1F_RING 32                 // records per thread ring
-#define K1F_RSTRIDE 33              // ring stride in records (padding against bank conflicts)
-#define K1F_ROW 16                  // records per flushed row (128 bytes)
+#define K1F_RING 16                 // records per thread ring
+#define K1F_RSTRIDE 17              // ring stride in records (padding against bank conflicts)
+#define K1F_ROW 8                   // records per flushed row (64 bytes = two full sectors)
 
 struct K1FastState {
     uint32_t suf[9];
@@ -244,6 +244,38 @@ __device__ __forceinline__ void k1_fast_block(K1FastState &S, uint32_t ch, int n
     S.base += 8;
 }
 
+// Steady-state block (every slot >= w-1): no warm-up tests, k-mer codes by funnel shift out of
+// (previous code : 8 new bases), and the record is stored unconditionally at ring[n_out] -- the
+// index only advances when the window minimum changed, otherwise the next store overwrites it.
+__device__ __forceinline__ void k1_fast_block_steady(K1FastState &S, uint32_t ch, uint32_t kmask,
+                                                     uint2 *__restrict__ ring)
+{
+    const uint32_t lo = (S.code << 16) | ch, hi = S.code >> 16;
+    uint32_t key[8];
+    uint32_t pm = K1F_INF;
+    const uint32_t base = (uint32_t)S.base;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const uint32_t c = __funnelshift_r(lo, hi, 14 - 2 * t) & kmask;
+        const uint32_t kk = (c << 4) | (uint32_t)(8 + t);
+        key[t] = kk;
+        pm = min(pm, kk);
+        const uint32_t m = min(S.suf[t + 1], pm);
+        ring[S.n_out & (K1F_RING - 1)] = make_uint2(m, base);
+        S.n_out += (m != S.last_key) ? 1u : 0u;
+        S.last_key = m;
+    }
+    S.code = lo & kmask;
+    uint32_t sm = K1F_INF;
+#pragma unroll
+    for (int t = 7; t >= 0; --t) {
+        sm = min(sm, key[t]);
+        S.suf[t] = sm - 8u;
+    }
+    S.last_key = (S.last_key & 8u) ? S.last_key - 8u : (K1F_INF - 1u);
+    S.base += 8;
+}
+
 // decode a ring record: key = code << 4 | tag, tag 0..7 = previous block, 8..15 = block at `base`
 __device__ __forceinline__ Minimizer k1_fast_decode(uint2 rec, int k)
 {
@@ -284,42 +316,48 @@ k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ 
 #pragma unroll
     for (int t = 0; t < 9; ++t) S.suf[t] = K1F_INF;
     S.code = 0; S.base = 0; S.last_key = K1F_INF - 1u; S.n_out = 0;
-    unsigned long long fifo = 0, inbuf = 0;
+    uint32_t fifo = 0;                          // <= 16 kept bases, newest in the low bits
+    unsigned long long inbuf = 0;
     int avail = 0, inleft = 0;                  // bytes left in inbuf
     int bytes_left = L >> 2;                    // whole bytes (4 bases) of input still to consume
     int next_pair = 0;                          // next uint2 (8 bytes = 32 bases) to load
-    uint32_t prev = 0, n_fl = 0;
-    bool first = true, tail_done = (L == 0);
+    const int n_pairs = (L + 31) >> 5;
+    uint2 ahead = (have && n_pairs > 0) ? __ldg(pk) : make_uint2(0, 0);
+    uint32_t prev = have ? ((ahead.x >> 30) ^ 1u) : 0u, n_fl = 0;
+    bool tail_done = (L == 0);
     bool active = have;
+
+#define K1F_LOAD_PAIR()                                                              \
+    do {                                                                             \
+        inbuf = ((unsigned long long)ahead.x << 32) | ahead.y;                       \
+        inleft = 8;                                                                  \
+        ++next_pair;                                                                 \
+        if (next_pair < n_pairs) ahead = __ldg(pk + next_pair);                      \
+    } while (0)
+#define K1F_LUT_STEP()                                                               \
+    do {                                                                             \
+        if (inleft == 0) K1F_LOAD_PAIR();                                            \
+        const uint32_t byte_ = (uint32_t)(inbuf >> 56);                              \
+        inbuf <<= 8; --inleft; --bytes_left;                                         \
+        const uint32_t e_ = lut[(prev << 8) | byte_];                                \
+        const uint32_t c_ = e_ >> 8;                                                 \
+        fifo = (fifo << (2 * c_)) | (e_ & 255u);                                     \
+        avail += (int)c_;                                                            \
+        prev = byte_ & 3u;                                                           \
+    } while (0)
 
     while (__any_sync(NGSID_FULL_MASK, active)) {
         if (active) {
-            // ---- refill the FIFO up to >= 8 kept bases
-            while (avail < 8 && bytes_left > 0) {
-                if (inleft == 0) {
-                    const uint2 v = __ldg(pk + next_pair++);
-                    inbuf = ((unsigned long long)v.x << 32) | v.y;
-                    inleft = 8;
-                    if (first) { prev = (v.x >> 30) ^ 1u; first = false; }
-                }
-                const uint32_t byte = (uint32_t)(inbuf >> 56);
-                inbuf <<= 8; --inleft; --bytes_left;
-                const uint32_t e = lut[(prev << 8) | byte];
-                const uint32_t c = e >> 8;
-                fifo = (fifo << (2 * c)) | (unsigned long long)(e & 255u);
-                avail += (int)c;
-                prev = byte & 3u;
-            }
+            // ---- refill: three straight-line table steps cover the average demand (8 kept bases per
+            // block ~ 2.7 input bytes); the loop behind them only runs after long homopolymers
+#pragma unroll
+            for (int st = 0; st < 3; ++st)
+                if (avail <= 12 && bytes_left > 0) K1F_LUT_STEP();
+            while (avail < 8 && bytes_left > 0) K1F_LUT_STEP();
             if (avail < 8 && !tail_done) {
-                // the last 0..3 bases of the read sit in the next byte
-                const int rem = L & 3;
+                const int rem = L & 3;          // the last 0..3 bases sit in the next byte
                 if (rem) {
-                    if (inleft == 0) {
-                        const uint2 v = __ldg(pk + next_pair++);
-                        inbuf = ((unsigned long long)v.x << 32) | v.y;
-                        inleft = 8;
-                        if (first) { prev = (v.x >> 30) ^ 1u; first = false; }
-                    }
+                    if (inleft == 0) K1F_LOAD_PAIR();
                     uint32_t byte = (uint32_t)(inbuf >> 56);
                     for (int t = 0; t < rem; ++t) {
                         const uint32_t b = (byte >> 6) & 3u;
@@ -331,13 +369,13 @@ k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ 
                 tail_done = true;
             }
             if (avail >= 8) {
-                const uint32_t ch = (uint32_t)(fifo >> (2 * (avail - 8))) & 0xffffu;
+                const uint32_t ch = (fifo >> (2 * (avail - 8))) & 0xffffu;
                 avail -= 8;
-                k1_fast_block<false>(S, ch, 8, k, w, kmask, ring);
+                if (S.base >= w) k1_fast_block_steady(S, ch, kmask, ring);
+                else k1_fast_block<false>(S, ch, 8, k, w, kmask, ring);
             } else {
-                // input exhausted: last partial block, then this lane is done
-                if (avail > 0) {
-                    const uint32_t ch = (uint32_t)(fifo << (2 * (8 - avail))) & 0xffffu;
+                if (avail > 0) {                // input exhausted: last partial block
+                    const uint32_t ch = (fifo << (2 * (8 - avail))) & 0xffffu;
                     const int nv = avail;
                     avail = 0;
                     k1_fast_block<true>(S, ch, nv, k, w, kmask, ring);
@@ -346,25 +384,28 @@ k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ 
                 active = false;
             }
         }
-        // ---- flush full rows of 16 records, two rows per round (16 lanes x 8 bytes each)
+        // ---- flush full rows of 8 records; eight rows per round, 4 lanes x 16 bytes per row
         uint32_t fm = __ballot_sync(NGSID_FULL_MASK, have && (S.n_out - n_fl) >= K1F_ROW);
         while (fm) {
-            const int l0 = __ffs(fm) - 1;
-            fm &= fm - 1;
-            int l1 = -1;
-            if (fm) { l1 = __ffs(fm) - 1; fm &= fm - 1; }
-            const int leader = (lane < 16) ? l0 : l1;
+            // each group of 4 lanes serves the first of its own lanes that has a full row
+            const uint32_t gm = (fm >> (lane & ~3)) & 15u;
+            const int leader = gm ? ((lane & ~3) + __ffs(gm) - 1) : -1;
+            const bool is_leader = (leader == lane);
+            fm = __ballot_sync(NGSID_FULL_MASK, ((fm >> lane) & 1u) && !is_leader);
             const int src = leader >= 0 ? leader : 0;
             const uint32_t fl = __shfl_sync(NGSID_FULL_MASK, n_fl, src);
             const unsigned long long op = __shfl_sync(NGSID_FULL_MASK, (unsigned long long)out, src);
             if (leader >= 0) {
-                const int e = lane & 15;
-                const uint2 rec = rings[(threadIdx.x - lane + leader) * K1F_RSTRIDE + ((fl + e) & (K1F_RING - 1))];
-                reinterpret_cast<Minimizer *>(op)[fl + e] = k1_fast_decode(rec, k);
+                const int e = (lane & 3) * 2;
+                const uint2 *rp = rings + (threadIdx.x - lane + leader) * K1F_RSTRIDE + ((fl + e) & (K1F_RING - 1));
+                const Minimizer a = k1_fast_decode(rp[0], k), b = k1_fast_decode(rp[1], k);
+                reinterpret_cast<uint4 *>(reinterpret_cast<Minimizer *>(op) + fl)[lane & 3] = make_uint4(a.x, a.y, b.x, b.y);
             }
-            if (lane == l0 || lane == l1) n_fl += K1F_ROW;
+            if (is_leader) n_fl += K1F_ROW;
         }
     }
+#undef K1F_LUT_STEP
+#undef K1F_LOAD_PAIR
     if (!have) return;
     const int Lc = S.base;
     if (Lc < w) {

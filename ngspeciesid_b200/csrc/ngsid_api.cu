@@ -158,7 +158,7 @@ static int k1_prepare(ngsid_ctx *ctx, int k, int w)
     for (int64_t i = 0; i < n; ++i) {
         ctx->h_moff[i] = s;
         int64_t L = ctx->h_off[i + 1] - ctx->h_off[i];
-        s += (std::max<int64_t>(1, L - w + 1) + 15) / 16 * 16;     // rows of 16 records stay 128-byte aligned
+        s += (std::max<int64_t>(1, L - w + 1) + 7) / 8 * 8;        // rows of 8 records stay 64-byte aligned
     }
     ctx->h_moff[n] = s;
     CUDA_TRY(ctx, ctx->d_moff.ensure((n + 1) * sizeof(int64_t)));

@@ -346,7 +346,7 @@ def test_k1_properties_at_scale(eng):
     k, w = 13, 20
     eng.minimizers(k, w)
     len_c, counts, kmer, pos = eng.get_minimizers()
-    starts = np.concatenate([[0], np.cumsum(counts)])
+    starts = np.concatenate([[0], np.cumsum(counts.astype(np.int64))])
     assert (counts > 0).all()
     d = np.diff(pos.astype(np.int64))
     boundary = np.zeros(len(pos), dtype=bool)
