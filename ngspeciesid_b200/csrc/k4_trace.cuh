@@ -165,6 +165,13 @@ struct K4TStat {
     }
 };
 
+// One WARP per pair. The path visits the 128-byte trace rows (one per wavefront step) in strictly
+// descending order -- a diagonal or horizontal move goes to row t-1 of the same lane strip, a
+// vertical move stays in the row or goes to row t-1 of the strip above -- so the warp streams the
+// rows with coalesced loads, keeps K4T_PF rows in flight, and every lane follows the (uniform)
+// state machine taking the word it needs by shuffle.
+#define K4T_PF 8
+
 __global__ void __launch_bounds__(128)
 k4t_traceback_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
                      const int32_t *__restrict__ pb, const int32_t *__restrict__ pm, int stride,
@@ -174,7 +181,8 @@ k4t_traceback_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
                      int32_t *__restrict__ out_match, int32_t *__restrict__ out_cols,
                      K4TWindow *__restrict__ out_win, int window)
 {
-    const int64_t sl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = (int)lane_id();
+    const int64_t sl = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (sl >= n_pairs) return;
     const int64_t pr = pair0 + sl;
     const int ra = pa[pr * stride], rb = pb[pr * stride];
@@ -187,42 +195,61 @@ k4t_traceback_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
     S.hist = 0; S.ncol = 0; S.cnt = 0; S.k = k; S.m = pm ? pm[pr * stride] : 1;
     S.hm = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
     int n_match = 0, n_cols = 0;
-    K4TWindow win[K4T_MAXWIN];
+    // window breaking points: lane w keeps window w (K4T_MAXWIN <= 32)
     const int nwin = out_win ? min(K4T_MAXWIN, (n2 + window - 1) / window) : 0;
-    for (int w = 0; w < nwin; ++w) { win[w].q_first = win[w].q_last = win[w].t_first = win[w].t_last = -1; }
+    K4TWindow mywin; mywin.q_first = mywin.q_last = mywin.t_first = mywin.t_last = -1;
 
-    // columns are visited from the last to the first; the window statistic is symmetric
     const int trailing = (n1 - 1 - e.end_i) + (n2 - 1 - e.end_j);
     for (int t = 0; t < trailing; ++t) S.push(0u);
     n_cols += trailing;
     int i = e.end_i, j = e.end_j, state = 0;            // 0 = H, 2 = D, 3 = I
     while (i >= 0 && j >= 0) {
-        const int lane = (i & 255) >> 3;
-        const uint32_t word = tr[((size_t)(i >> 8) * nsteps + (size_t)(j + lane)) * 32 + lane];
-        const uint32_t nib = (word >> (4 * (i & 7))) & 15u;
-        if (state == 0) {
-            const uint32_t c = nib & 3u;
-            if (c <= 1u) {
-                S.push(c == 0u ? 1u : 0u);
-                n_match += (c == 0u);
-                n_cols++;
-                if (nwin) {
-                    const int w = j / window;
-                    if (w < nwin) {
-                        if (win[w].q_last < 0) { win[w].q_last = i + 1; win[w].t_last = j + 1; }
-                        win[w].q_first = i; win[w].t_first = j;
+        // rows of the current pass, from the current one downwards, K4T_PF at a time
+        const int pass = i >> 8;
+        const uint32_t *tp = tr + (size_t)pass * nsteps * 32;
+        int t_cur = j + ((i & 255) >> 3);
+        uint32_t buf[K4T_PF];
+#pragma unroll
+        for (int q = 0; q < K4T_PF; ++q) buf[q] = (t_cur - q >= 0) ? __ldcs(tp + (size_t)(t_cur - q) * 32 + lane) : 0u;
+        int t_top = t_cur;                               // buf[q] holds row t_top - q
+        while (i >= 0 && j >= 0 && (i >> 8) == pass) {
+            const int strip = (i & 255) >> 3;
+            const int t = j + strip;
+            if (t_top - t >= K4T_PF) {                   // refill the window of rows
+                t_top = t;
+#pragma unroll
+                for (int q = 0; q < K4T_PF; ++q) buf[q] = (t_top - q >= 0) ? __ldcs(tp + (size_t)(t_top - q) * 32 + lane) : 0u;
+            }
+            uint32_t mine = 0;
+            const int sel = t_top - t;
+#pragma unroll
+            for (int q = 0; q < K4T_PF; ++q) if (q == sel) mine = buf[q];
+            const uint32_t word = __shfl_sync(NGSID_FULL_MASK, mine, strip);
+            const uint32_t nib = (word >> (4 * (i & 7))) & 15u;
+            if (state == 0) {
+                const uint32_t c = nib & 3u;
+                if (c <= 1u) {
+                    S.push(c == 0u ? 1u : 0u);
+                    n_match += (c == 0u);
+                    n_cols++;
+                    if (nwin) {
+                        const int w = j / window;
+                        if (lane == w) {
+                            if (mywin.q_last < 0) { mywin.q_last = i + 1; mywin.t_last = j + 1; }
+                            mywin.q_first = i; mywin.t_first = j;
+                        }
                     }
-                }
-                --i; --j;
-            } else state = (int)c;
-        } else if (state == 2) {
-            S.push(0u); n_cols++;
-            if (nib & 4u) state = 0;
-            --j;
-        } else {
-            S.push(0u); n_cols++;
-            if (nib & 8u) state = 0;
-            --i;
+                    --i; --j;
+                } else state = (int)c;
+            } else if (state == 2) {
+                S.push(0u); n_cols++;
+                if (nib & 4u) state = 0;
+                --j;
+            } else {
+                S.push(0u); n_cols++;
+                if (nib & 8u) state = 0;
+                --i;
+            }
         }
     }
     const int leading = (i + 1) + (j + 1);
@@ -230,12 +257,14 @@ k4t_traceback_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
     n_cols += leading;
     int cnt = S.cnt;
     if (n_cols < k) cnt = (__popc(S.hist) >= S.m) ? 1 : 0;
-    if (out_count) out_count[pr] = cnt;
-    if (out_score) out_score[pr] = e.score;
-    if (out_match) out_match[pr] = n_match;
-    if (out_cols) out_cols[pr] = n_cols;
-    if (out_win) for (int w = 0; w < K4T_MAXWIN; ++w) {
+    if (lane == 0) {
+        if (out_count) out_count[pr] = cnt;
+        if (out_score) out_score[pr] = e.score;
+        if (out_match) out_match[pr] = n_match;
+        if (out_cols) out_cols[pr] = n_cols;
+    }
+    if (out_win && lane < K4T_MAXWIN) {
         K4TWindow x; x.q_first = x.q_last = x.t_first = x.t_last = -1;
-        out_win[pr * K4T_MAXWIN + w] = (w < nwin) ? win[w] : x;
+        out_win[pr * K4T_MAXWIN + lane] = (lane < nwin) ? mywin : x;
     }
 }

@@ -398,7 +398,7 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
                                                                ctx->d_trace.as<uint32_t>(), slot_words,
                                                                ctx->d_ends.as<K4TEnd>());
         KERNEL_CHECK(ctx);
-        k4t_traceback_kernel<<<(unsigned)((c + 127) / 128), 128, 0, ctx->stream>>>(
+        k4t_traceback_kernel<<<(unsigned)((c + 3) / 4), 128, 0, ctx->stream>>>(
             Q, pa, pb, pm, stride, p0, c, k, ctx->d_trace.as<uint32_t>(), slot_words, ctx->d_ends.as<K4TEnd>(),
             out_count, out_score, out_match, out_cols, out_win, window);
         KERNEL_CHECK(ctx);
