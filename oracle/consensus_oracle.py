@@ -33,6 +33,11 @@ def _lib():
         lib.oracle_poa_consensus.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+        lib.oracle_poa_consensus_ex.restype = ctypes.c_int
+        lib.oracle_poa_consensus_ex.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
+                                                ctypes.POINTER(ctypes.c_int)]
         lib.oracle_sg_align.restype = ctypes.c_int
         lib.oracle_sg_align.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -42,7 +47,10 @@ def _lib():
     return lib
 
 
-def poa_consensus(seqs, quals=None, mode=0, match=5, mismatch=-4, gap=-2, trim=False):
+ORDER_MODE = 0        # 0 = spoa's re-sort (reference-faithful), 1 = path insertion (the kernel's order)
+
+
+def poa_consensus(seqs, quals=None, mode=0, match=5, mismatch=-4, gap=-2, trim=False, order_mode=None):
     n = len(seqs)
     arr = (ctypes.c_char_p * n)(*[s.encode() for s in seqs])
     qarr = None
@@ -51,7 +59,8 @@ def poa_consensus(seqs, quals=None, mode=0, match=5, mismatch=-4, gap=-2, trim=F
     cap = sum(len(s) for s in seqs) + 16
     out = ctypes.create_string_buffer(cap)
     nn = ctypes.c_int(0)
-    r = _lib().oracle_poa_consensus(arr, qarr, n, mode, match, mismatch, gap, 1 if trim else 0, out, cap, ctypes.byref(nn))
+    om = ORDER_MODE if order_mode is None else order_mode
+    r = _lib().oracle_poa_consensus_ex(arr, qarr, n, mode, match, mismatch, gap, 1 if trim else 0, om, out, cap, ctypes.byref(nn))
     if r < 0:
         raise MemoryError("oracle_poa_consensus")
     return out.value.decode()

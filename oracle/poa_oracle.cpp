@@ -45,6 +45,7 @@ struct Graph {
     std::vector<int> rank;                      // node -> rank
     std::vector<int> coverage;                  // sequences through the node
     int n_seqs = 0;
+    int order_mode = 0;                         // 0: spoa's DFS sort after every sequence, 1: path insertion
 
     int add_node(char c) {
         letter.push_back(c); in.emplace_back(); out.emplace_back(); aligned.emplace_back();
@@ -185,21 +186,57 @@ static std::vector<Pair> align(const Graph &G, const char *s, int L, int mode, i
     return aln;
 }
 
+// Order maintenance without a full sort ("path insertion"): a run of new nodes between the old
+// path nodes p and s goes immediately after p (in path order); a run at the start of the path
+// goes immediately before s; a path without old nodes is appended. The alignment is monotone in
+// the current order, so the result is again a topological order.
+static void insert_path_order(Graph &G, const std::vector<int> &path, int old_V)
+{
+    std::vector<int> run;
+    int last_old = -1;
+    auto place_after = [&](int p, const std::vector<int> &r) {
+        auto it = std::find(G.order.begin(), G.order.end(), p);
+        G.order.insert(it + 1, r.begin(), r.end());
+    };
+    for (size_t i = 0; i < path.size(); ++i) {
+        const int v = path[i];
+        if (v >= old_V) { run.push_back(v); continue; }
+        if (!run.empty()) {
+            if (last_old >= 0) place_after(last_old, run);
+            else { auto it = std::find(G.order.begin(), G.order.end(), v); G.order.insert(it, run.begin(), run.end()); }
+            run.clear();
+        }
+        last_old = v;
+    }
+    if (!run.empty()) {
+        if (last_old >= 0) place_after(last_old, run);
+        else G.order.insert(G.order.end(), run.begin(), run.end());
+    }
+    G.rank.assign(G.letter.size(), 0);
+    for (size_t r = 0; r < G.order.size(); ++r) G.rank[G.order[r]] = (int)r;
+}
+
 static void add_alignment(Graph &G, const std::vector<Pair> &aln, const char *s, const int *wt, int L)
 {
     if (L == 0) return;
+    const int old_V = (int)G.letter.size();
+    std::vector<int> path;
     std::vector<int> valid;
     for (const Pair &p : aln) if (p.pos >= 0) valid.push_back(p.pos);
     if (valid.empty()) {
         G.add_chain(s, wt, 0, L);
         G.n_seqs++;
-        G.topo_sort();
+        if (G.order_mode == 0) G.topo_sort();
+        else { for (int v = old_V; v < (int)G.letter.size(); ++v) path.push_back(v); insert_path_order(G, path, old_V); }
         return;
     }
     const int before = (int)G.letter.size();
     G.add_chain(s, wt, 0, valid.front());
     int head = ((int)G.letter.size() == before) ? -1 : (int)G.letter.size() - 1;
+    for (int v = before; v < (int)G.letter.size(); ++v) path.push_back(v);
+    const int tail_first_id = (int)G.letter.size();
     int tail = G.add_chain(s, wt, valid.back() + 1, L);
+    const int tail_end_id = (int)G.letter.size();
     long long prev_w = head == -1 ? 0 : wt[valid.front() - 1];
     for (const Pair &p : aln) {
         if (p.pos < 0) continue;
@@ -220,13 +257,16 @@ static void add_alignment(Graph &G, const std::vector<Pair> &aln, const char *s,
             }
         }
         G.coverage[node]++;
+        path.push_back(node);
         if (head != -1) G.add_edge(head, node, prev_w + wt[p.pos]);
         head = node;
         prev_w = wt[p.pos];
     }
     if (tail != -1) G.add_edge(head, tail, prev_w + wt[valid.back() + 1]);
+    for (int v = tail_first_id; v < tail_end_id; ++v) path.push_back(v);
     G.n_seqs++;
-    G.topo_sort();
+    if (G.order_mode == 0) G.topo_sort();
+    else insert_path_order(G, path, old_V);
 }
 
 static std::vector<int> heaviest_bundle(const Graph &G)
@@ -284,10 +324,23 @@ extern "C" {
  * trim != 0 applies racon's coverage trimming to the consensus ends (coverage >= (n-1)/2).
  * Returns the consensus length (written to out, capacity cap) or -1.
  */
+int oracle_poa_consensus_ex(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                            int trim, int order_mode, char *out, int cap, int *n_nodes_out);
+
 int oracle_poa_consensus(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
                          int trim, char *out, int cap, int *n_nodes_out)
 {
+    return oracle_poa_consensus_ex(seqs, quals, n, mode, m, x, g, trim, 0, out, cap, n_nodes_out);
+}
+
+/* order_mode 0: spoa's topological re-sort after every sequence (reference-faithful);
+ * order_mode 1: "path insertion" order maintenance (what the CUDA kernel does; any topological
+ * order gives a valid POA, the two differ only in tie-breaks between equal scores). */
+int oracle_poa_consensus_ex(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                            int trim, int order_mode, char *out, int cap, int *n_nodes_out)
+{
     Graph G;
+    G.order_mode = order_mode;
     std::vector<int> wt;
     for (int i = 0; i < n; ++i) {
         const int L = (int)strlen(seqs[i]);
