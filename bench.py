@@ -415,7 +415,7 @@ def run_ours(args):
         except Exception:
             pass
         achieved = alg_bytes / (ms / 1000.0) / 1e9
-        result["roofline"] = {"kernel": "k1_fast_kernel (thread per read)", "bound": "hbm", "achieved": achieved, "peak": peak,
+        result["roofline"] = {"kernel": "k1_stream_kernel (thread per read: compress + window minima; warp per 32 reads: output)", "bound": "hbm", "achieved": achieved, "peak": peak,
                               "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                               "reads_per_launch": int(len(blens)), "bytes_per_read": alg_bytes / len(blens),
                               "kernel_ms": ms, "reads_per_s": len(blens) / (ms / 1000.0)}

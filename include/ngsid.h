@@ -46,8 +46,10 @@ int ngsid_sync(ngsid_ctx *ctx);
  * 4 sum of K4 launches inside the last clustering pass, 5 sum of map launches inside it.
  * Returns a negative value when that phase has not run.                                        */
 float ngsid_phase_ms(ngsid_ctx *ctx, int which);
-/* Tuning / test switches. option 1: value != 0 forces the generic warp-per-read K1 kernel for
- * every (k, w) (the thread-per-read fast kernel otherwise serves w-k+1 == 8, k <= 13).         */
+/* Tuning / test switches. option 1 selects the K1 kernel: 0 (default) the stream kernel for
+ * w-k+1 == 8, k <= 13 and the generic warp-per-read kernel otherwise; 1 the generic kernel for
+ * every (k, w); 2 the older thread-per-read ring kernel instead of the stream kernel.
+ * option 2: value != 0 selects the trace-free payload variant of K4.                           */
 int ngsid_set_option(ngsid_ctx *ctx, int option, int value);
 
 /* ---- read upload ---------------------------------------------------------------------------

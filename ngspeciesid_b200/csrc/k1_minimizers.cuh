@@ -7,7 +7,9 @@
 // ---------------------------------------------------------------------------------------------
 // K_pack: ASCII -> 2 bit/base, first base in the most significant bits of each u32 word.
 // A,C,G,T -> 0,1,2,3 (ASCII order, so unsigned compare of codes == string compare). Any other
-// byte raises the error flag (this build handles the ACGT alphabet only).
+// byte raises the error flag (this build handles the ACGT alphabet only). The unused tail of a
+// read's last word repeats the read's last base, so the tail never starts a new homopolymer run
+// (k1_stream_kernel compresses whole words).
 __global__ void k_pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off,
                               const int64_t *__restrict__ woff, uint32_t *__restrict__ packed,
                               int64_t n_reads, int *__restrict__ bad_flag)
@@ -25,12 +27,11 @@ __global__ void k_pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__
             int base = wi << 4;
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-                int b = base + t;
-                uint32_t c = (b < L) ? s[b] : (uint32_t)'A';
+                int b = min(base + t, L - 1);
+                uint32_t c = s[b];
                 bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
                 if (!ok) *bad_flag = 1;
                 uint32_t code = ((c >> 1) & 3u) ^ ((c >> 2) & 1u);
-                if (b >= L) code = 0;
                 word |= code << (30 - 2 * t);
             }
             out[wi] = word;

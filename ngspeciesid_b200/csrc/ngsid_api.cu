@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "ngsid_internal.cuh"
 #include "k1_minimizers.cuh"
+#include "k1_stream.cuh"
 #include "k2_map.cuh"
 #include "k4_align.cuh"
 #include "k4_trace.cuh"
@@ -53,7 +54,12 @@ extern "C" float ngsid_phase_ms(ngsid_ctx *ctx, int which)
 extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
 {
     if (!ctx) return NGSID_EINVAL;
-    if (option == 1) { ctx->force_generic_k1 = value != 0; ctx->have_min = false; return NGSID_OK; }
+    if (option == 1) {
+        if (value < 0 || value > 2) return fail(ctx, NGSID_EINVAL, "option 1 takes 0, 1 or 2");
+        ctx->k1_variant = value == 0 ? 2 : value == 1 ? 0 : 1;
+        ctx->have_min = false;
+        return NGSID_OK;
+    }
     if (option == 2) { ctx->use_payload_k4 = value != 0; return NGSID_OK; }
     return fail(ctx, NGSID_EINVAL, "unknown option");
 }
@@ -196,18 +202,30 @@ static int k1_launch_generic(ngsid_ctx *ctx, const int32_t *list, const int32_t 
 
 static int k1_launch(ngsid_ctx *ctx)
 {
-    const bool fast = (ctx->w - ctx->k + 1 == 8) && ctx->k <= 13 && !ctx->force_generic_k1;
+    const bool fast = (ctx->w - ctx->k + 1 == 8) && ctx->k <= 13 && ctx->k >= 2 && ctx->k1_variant != 0;
     if (!fast) return k1_launch_generic(ctx, nullptr, nullptr, ctx->n_reads);
-    // fast path + hand-over list for reads with compressed length < w
+    // fast path + hand-over list for reads with a short compressed length
     CUDA_TRY(ctx, ctx->d_newslots.ensure((size_t)(ctx->n_reads + 16) * 4));
     int32_t *slow_n = ctx->d_newslots.as<int32_t>();
     int32_t *slow_list = slow_n + 4;
     CUDA_TRY(ctx, cudaMemsetAsync(slow_n, 0, 16, ctx->stream));
-    int blocks = (int)((ctx->n_reads + 127) / 128);
-    k1_fast_kernel<<<blocks, 128, 0, ctx->stream>>>(
-        ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
-        ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
-        ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, slow_list, slow_n);
+    const K1SGeom g = k1s_geometry(ctx->max_len, ctx->k);
+    const size_t smem = k1s_smem_bytes(g);
+    if (ctx->k1_variant == 2 && smem <= K1S_SMEM_LIMIT && g.n_it_max + 2 <= 255) {   // staged positions are 13 bits
+        // stream kernel: thread per read for compression + window minima, warp per 32 reads for output
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int blocks = (int)((ctx->n_reads + K1S_THREADS - 1) / K1S_THREADS);
+        k1_stream_kernel<<<blocks, K1S_THREADS, smem, ctx->stream>>>(
+            ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
+            ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
+            ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, g.sw, g.bw, g.rs, g.scap, slow_list, slow_n);
+    } else {
+        int blocks = (int)((ctx->n_reads + 127) / 128);
+        k1_fast_kernel<<<blocks, 128, 0, ctx->stream>>>(
+            ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
+            ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
+            ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, slow_list, slow_n);
+    }
     KERNEL_CHECK(ctx);
     return k1_launch_generic(ctx, slow_list, slow_n, std::min<int64_t>(ctx->n_reads, 4096));
 }

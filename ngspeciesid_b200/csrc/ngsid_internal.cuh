@@ -57,7 +57,7 @@ struct ngsid_ctx {
     int k = 0, w = 0;
     bool have_min = false;
     bool use_payload_k4 = false;      // option 2: the trace-free payload kernel instead of DP + traceback
-    bool force_generic_k1 = false;    // tests: run the warp-per-read kernel for every (k,w)
+    int k1_variant = 2;               // 2: stream kernel (default), 1: thread-per-read ring kernel, 0: generic warp-per-read kernel for every (k,w)
     std::vector<int64_t> h_moff;      // n+1 offsets into d_mins (slack CSR: capacity per read)
     std::vector<uint32_t> h_nmin;     // mirror of d_nmin (filled lazily)
     bool h_nmin_valid = false;

@@ -40,11 +40,12 @@ def _check_minimizers(eng, seqs, k, w):
 def test_k1_minimizers_fixtures(eng, tag, k, w):
     seqs = [s for _a, s, _q in scenario_reads(tag)]
     _check_minimizers(eng, seqs, k, w)
-    eng.set_option(1, 1)                # the generic warp-per-read kernel must agree as well
-    try:
-        _check_minimizers(eng, seqs, k, w)
-    finally:
-        eng.set_option(1, 0)
+    for variant in (1, 2):              # the generic warp-per-read and the ring kernels must agree as well
+        eng.set_option(1, variant)
+        try:
+            _check_minimizers(eng, seqs, k, w)
+        finally:
+            eng.set_option(1, 0)
 
 
 @pytest.mark.parametrize("k,w", [(13, 20), (12, 19), (5, 12), (2, 9)])
