@@ -61,6 +61,11 @@ extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
         return NGSID_OK;
     }
     if (option == 2) { ctx->use_payload_k4 = value != 0; return NGSID_OK; }
+    if (option == 3) {
+        if (value < 0 || value > 2) return fail(ctx, NGSID_EINVAL, "option 3 takes 0, 1 or 2");
+        ctx->k4_shape = value;
+        return NGSID_OK;
+    }
     return fail(ctx, NGSID_EINVAL, "unknown option");
 }
 
@@ -393,14 +398,34 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
 {
     if (n_pairs == 0) return NGSID_OK;
     int n2cap = ((max_n2 + 15) / 16) * 16 + 16;
+    // throughput shape: one warp per pair
     size_t per_warp = k4t_smem_per_warp(n2cap);
     int wpb = (int)std::min<size_t>(4, SMEM_BUDGET / per_warp);
     if (wpb < 1) return fail(ctx, NGSID_EUNSUPPORTED, "sequence too long for the K4 shared-memory row buffer");
     size_t smem = per_warp * wpb;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k4t_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k4t_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int bps = 1;
-    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k4t_dp_kernel, wpb * 32, smem));
+    CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k4t_dp_kernel<false>, wpb * 32, smem));
     bps = std::max(1, bps);
+    // latency shape: one block of W warps per pair (small rounds of the greedy pass)
+    const int npass_max = (max_n1 + 32 * K4T_RPL - 1) / (32 * K4T_RPL);
+    const int W = std::max(1, std::min(K4T_MAXW, npass_max));
+    const size_t smem_multi = k4t_smem_multi(n2cap, W);
+    const bool multi_ok = W > 1 && smem_multi <= SMEM_BUDGET;
+    int bps_multi = 1;
+    if (multi_ok) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k4t_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_multi));
+        CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps_multi, k4t_dp_kernel<true>, W * 32, smem_multi));
+        bps_multi = std::max(1, bps_multi);
+    }
+    // traceback: one warp per pair, shared-memory row ring + both sequences
+    const int ncap = ((std::max(max_n1, max_n2) + 15) / 16) * 16 + 16;
+    const size_t tb_per_warp = k4t_tb_smem_per_warp(ncap);
+    int tb_wpb = (int)std::min<size_t>(4, SMEM_BUDGET / tb_per_warp);
+    if (tb_wpb < 1) return fail(ctx, NGSID_EUNSUPPORTED, "sequence too long for the K4 traceback buffers");
+    const size_t tb_smem = tb_per_warp * tb_wpb;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k4t_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+
     const size_t slot_words = k4t_trace_words(max_n1, max_n2);
     const size_t budget = (size_t)4 << 30;
     int64_t slots = (int64_t)std::max<size_t>(1, budget / (slot_words * 4));
@@ -411,14 +436,24 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
                  have_aux ? ctx->d_auxseq.as<uint8_t>() : nullptr, have_aux ? ctx->d_aoff.as<int64_t>() : nullptr};
     for (int64_t p0 = 0; p0 < n_pairs; p0 += slots) {
         const int64_t c = std::min<int64_t>(slots, n_pairs - p0);
-        int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c + wpb - 1) / wpb, (int64_t)ctx->sm_count * bps));
-        k4t_dp_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(Q, pa, pb, po, stride, p0, c, n2cap,
-                                                               ctx->d_trace.as<uint32_t>(), slot_words,
-                                                               ctx->d_ends.as<K4TEnd>());
+        // fewer pairs than the one-warp-per-pair shape needs to fill half the machine: take the latency shape
+        const bool multi = multi_ok && ctx->k4_shape != 1 &&
+                           (ctx->k4_shape == 2 || c * 2 <= (int64_t)ctx->sm_count * bps * wpb / W);
+        if (multi) {
+            int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c, (int64_t)ctx->sm_count * bps_multi));
+            k4t_dp_kernel<true><<<blocks, W * 32, smem_multi, ctx->stream>>>(Q, pa, pb, po, stride, p0, c, n2cap,
+                                                                             ctx->d_trace.as<uint32_t>(), slot_words,
+                                                                             ctx->d_ends.as<K4TEnd>());
+        } else {
+            int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((c + wpb - 1) / wpb, (int64_t)ctx->sm_count * bps));
+            k4t_dp_kernel<false><<<blocks, wpb * 32, smem, ctx->stream>>>(Q, pa, pb, po, stride, p0, c, n2cap,
+                                                                          ctx->d_trace.as<uint32_t>(), slot_words,
+                                                                          ctx->d_ends.as<K4TEnd>());
+        }
         KERNEL_CHECK(ctx);
-        k4t_traceback_kernel<<<(unsigned)((c + 3) / 4), 128, 0, ctx->stream>>>(
+        k4t_traceback_kernel<<<(unsigned)((c + tb_wpb - 1) / tb_wpb), tb_wpb * 32, tb_smem, ctx->stream>>>(
             Q, pa, pb, pm, stride, p0, c, k, ctx->d_trace.as<uint32_t>(), slot_words, ctx->d_ends.as<K4TEnd>(),
-            out_count, out_score, out_match, out_cols, out_win, window);
+            out_count, out_score, out_match, out_cols, out_win, window, ncap);
         KERNEL_CHECK(ctx);
     }
     return NGSID_OK;

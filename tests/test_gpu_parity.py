@@ -133,17 +133,28 @@ def _oracle_align(lib, a, b, o, k, m):
     return c, sc.value
 
 
-@pytest.mark.parametrize("payload_kernel", [0, 1])
-def test_k4_block_align_random_pairs(eng, payload_kernel):
+@pytest.mark.parametrize("payload_kernel,shape", [(0, 0), (0, 1), (0, 2), (1, 0)])
+def test_k4_block_align_random_pairs(eng, payload_kernel, shape):
     eng.set_option(2, payload_kernel)      # 0: DP + trace + traceback kernels, 1: trace-free payload kernel
+    eng.set_option(3, shape)               # DP shape: 0 per launch, 1 warp per pair, 2 block per pair (pipelined strips)
     try:
         _k4_random_pairs(eng)
     finally:
         eng.set_option(2, 0)
+        eng.set_option(3, 0)
 
 
-def test_k4_paths_identity_and_windows(eng):
+@pytest.mark.parametrize("shape", [1, 2])
+def test_k4_paths_identity_and_windows(eng, shape):
     """Score, identity and window breaking points against the oracle's expanded CIGAR."""
+    eng.set_option(3, shape)
+    try:
+        _k4_paths(eng)
+    finally:
+        eng.set_option(3, 0)
+
+
+def _k4_paths(eng):
     from oracle import consensus_oracle as co
     rng = np.random.default_rng(5)
 
