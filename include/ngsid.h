@@ -173,7 +173,12 @@ typedef struct {
     int32_t match, mismatch, gap;
     int32_t trim;        /* racon's coverage trimming of the consensus ends */
     int32_t max_nodes;
-    int32_t reserved[2];
+    int32_t reserved[2]; /* [1]: kernel shape, 0 = wavefront kernel (falls back to the row kernel
+                          * when a graph outgrows its shared-memory ring), 1 = row kernel.
+                          * [0]: 0 = spoa's depth-first re-sort after every layer (both kernels);
+                          * 1 = experimental path-insertion order, row kernel only (not a valid
+                          * topological order once aligned alternates are reused -- kept for the
+                          * oracle comparison, never used by modules/).                          */
 } ngsid_poa_params;
 
 int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,

@@ -23,6 +23,7 @@ struct K5Args {
     const uint8_t *seq, *qual; const int64_t *off;
     const uint8_t *aux; const int64_t *aoff;
     int mode, m, x, g, trim;
+    int order_mode;             // 0: spoa's DFS re-sort after every layer, 1: path insertion
     uint8_t *arena; size_t graph_bytes;
     int Vcap, Ecap, Acap, Scap, Lmax, ring_rows;
     int32_t *H; size_t h_words;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
             const uint8_t *q = src >= 0 ? A.qual + A.off[src] + lb : nullptr;
             const int V = G.V;
             if (V == 0 || L == 0) {
-                if (tid == 0) poa_add_alignment(G, 0, s, q, L);
+                if (tid == 0) poa_add_alignment(G, 0, s, q, L, A.order_mode);
                 __syncthreads();
                 continue;
             }
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(K5_THREADS) k5_poa_kernel(K5Args A)
                 if (!(A.mode == 0 && bv == 0)) n_aln = poa_traceback(G, H, ld, s, A.mode, A.m, A.x, g, bi, bj);
                 long long t2 = clock64();
                 cyc_tb += t2 - t1;
-                poa_add_alignment(G, n_aln, s, q, L);
+                poa_add_alignment(G, n_aln, s, q, L, A.order_mode);
                 cyc_add += clock64() - t2;
                 s_go = (G.err == 0 && G.V + A.Lmax + 2 < G.Vcap) ? 1 : 0;
                 if (!s_go && G.err == 0) G.err = 1;

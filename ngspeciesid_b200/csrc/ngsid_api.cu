@@ -10,6 +10,7 @@
 #include "k4_align.cuh"
 #include "k4_trace.cuh"
 #include "k5_poa.cuh"
+#include "k5_wave.cuh"
 
 static const size_t SMEM_BUDGET = 200 * 1024;
 
@@ -590,7 +591,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     while (slots > 1 && (double)slots * (double)(h_words * 4 + gbytes) > 48e9) slots /= 2;
     CUDA_TRY(ctx, ctx->d_poa_arena.ensure(gbytes * slots));
     CUDA_TRY(ctx, ctx->d_poa_h.ensure(h_words * 4 * slots));
-    CUDA_TRY(ctx, ctx->d_poa_meta.ensure((size_t)Vcap * 20 * slots + 64));
+    CUDA_TRY(ctx, ctx->d_poa_meta.ensure((size_t)Vcap * 4 * K5W_FAST * slots + 64));    // row kernel: 20 B per row; wavefront kernel: K5W_FAST ints
     CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)n_jobs * out_stride));
     CUDA_TRY(ctx, ctx->d_poa_len.ensure((size_t)n_jobs * 4));
     CUDA_TRY(ctx, ctx->d_poa_nodes.ensure((size_t)n_jobs * 4));
@@ -622,7 +623,33 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         CUDA_TRY(ctx, ctx->d_win.ensure((size_t)n_jobs * 32));
         A.cycles = ctx->d_win.as<long long>();
     }
-    const int ring_rows = (int)std::max<size_t>(2, std::min<size_t>(64, (size_t)(160 * 1024) / ((size_t)(Lmax + 2) * sizeof(int))));
+    // shape: reserved[1] = 0 wavefront kernel (falls back to the row kernel when a graph outgrows
+    // its shared-memory ring), 1 row kernel. Topological order: spoa's re-sort after every layer;
+    // the row kernel can also run the experimental path-insertion rule (reserved[0] = 1).
+    bool use_wave = params->reserved[1] != 1;
+    A.order_mode = params->reserved[0] == 1 ? 1 : 0;
+    int err = 0;
+    if (use_wave) {
+        const size_t dir_bytes = (((size_t)(Vcap + 1) * (size_t)(Lmax + 1)) + 255) / 256 * 256;
+        CUDA_TRY(ctx, ctx->d_poa_dir.ensure(dir_bytes * slots));
+        K5WArgs Wa;
+        Wa.a = A;
+        Wa.dir = ctx->d_poa_dir.as<uint8_t>(); Wa.dir_bytes = dir_bytes;
+        const size_t wave_smem = 200 * 1024;
+        Wa.smem_words = (int)(wave_smem / 4);
+        CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
+        k5w_poa_kernel<<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);
+        KERNEL_CHECK(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (err == 6 || err == 7) {                 // ring too small / too many in-edges: row kernel
+            use_wave = false;
+            err = 0;
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_poa_err.p, 0, 64, ctx->stream));
+        }
+    }
+    if (!use_wave) {
+    int ring_rows = (int)std::max<size_t>(2, std::min<size_t>(64, (size_t)(160 * 1024) / ((size_t)(Lmax + 2) * sizeof(int))));
     A.ring_rows = ring_rows;
     const size_t k5_smem = (size_t)ring_rows * (Lmax + 2) * sizeof(int);
     const int cneed = (Lmax + K5_THREADS - 1) / K5_THREADS;
@@ -637,7 +664,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     else K5_LAUNCH(16);
 #undef K5_LAUNCH
     KERNEL_CHECK(ctx);
-    int err = 0;
+    }
     CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_seq, ctx->d_poa_out.p, (size_t)n_jobs * out_stride, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_len, ctx->d_poa_len.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -71,7 +71,7 @@ struct ngsid_ctx {
     // ---- clustering scratch (see cluster_driver.cuh)
     DevBuf d_keys, d_heads, d_nodes, d_cursor, d_slot_read, d_slot_pos, d_slot_state;
     DevBuf d_order, d_accrank, d_dec, d_aux, d_via, d_list, d_scratch, d_params;
-    DevBuf d_poa_arena, d_poa_meta, d_poa_h, d_poa_out, d_poa_len, d_poa_nodes, d_poa_err, d_job_off, d_lsrc, d_lbeg, d_llen;
+    DevBuf d_poa_dir, d_poa_arena, d_poa_meta, d_poa_h, d_poa_out, d_poa_len, d_poa_nodes, d_poa_err, d_job_off, d_lsrc, d_lbeg, d_llen;
     DevBuf d_trace, d_ends, d_auxseq, d_aoff, d_win, d_match, d_cols;
     DevBuf d_req, d_reqn, d_acache, d_k4cnt, d_k4score, d_newslots, d_pa, d_pb, d_po, d_pm;
 };

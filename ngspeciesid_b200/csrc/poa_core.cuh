@@ -250,7 +250,8 @@ POA_HD void poa_insert_path_order(PoaGraph &G, int old_V, const int32_t *path, i
 }
 
 // Adds a sequence along its alignment (n_aln pairs stored in reverse order in G.aln_*).
-// order_mode 0: spoa's full re-sort; 1: path insertion (see above).
+// order_mode 0: spoa's full re-sort; 1: path insertion (see above); 2: leave order/rank to the
+// caller (the wavefront kernel runs poa_topo_sort on shared-memory copies of the edge lists).
 POA_HD void poa_add_alignment(PoaGraph &G, int n_aln, const uint8_t *s, const uint8_t *q, int L, int order_mode = 0)
 {
     if (L == 0) return;
@@ -264,7 +265,7 @@ POA_HD void poa_add_alignment(PoaGraph &G, int n_aln, const uint8_t *s, const ui
         poa_add_chain(G, s, q, 0, L);
         G.n_seqs++;
         if (order_mode == 0) poa_topo_sort(G);
-        else { for (int v = old_V; v < G.V; ++v) path[n_path++] = v; poa_insert_path_order(G, old_V, path, n_path); }
+        else if (order_mode == 1) { for (int v = old_V; v < G.V; ++v) path[n_path++] = v; poa_insert_path_order(G, old_V, path, n_path); }
         return;
     }
     const int before = G.V;
@@ -310,7 +311,7 @@ POA_HD void poa_add_alignment(PoaGraph &G, int n_aln, const uint8_t *s, const ui
     for (int v = tail_first; v < tail_end; ++v) path[n_path++] = v;
     G.n_seqs++;
     if (order_mode == 0) poa_topo_sort(G);
-    else poa_insert_path_order(G, old_V, path, n_path);
+    else if (order_mode == 1) poa_insert_path_order(G, old_V, path, n_path);
 }
 
 POA_HD void poa_relax(PoaGraph &G, int v, bool skip_dead)

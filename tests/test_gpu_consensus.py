@@ -21,6 +21,25 @@ def eng():
     e.close()
 
 
+@pytest.fixture(autouse=True, params=["wave", "row"])
+def poa_shape(request, eng):
+    """Every test runs on the wavefront kernel and on the row kernel; both keep spoa's topological
+    re-sort after every layer (oracle order_mode 0)."""
+    from ngspeciesid_b200 import engine as E
+    old = co.ORDER_MODE
+    engines = [eng, E.get_engine(0)]              # the fixture's engine and the one modules/ share
+    shape = 0 if request.param == "wave" else 1
+    co.ORDER_MODE = 0
+    for e in engines:
+        e.poa_shape, e.poa_order_mode = shape, 0
+    try:
+        yield request.param
+    finally:
+        co.ORDER_MODE = old
+        for e in engines:
+            e.poa_shape, e.poa_order_mode = 0, 0
+
+
 def species_reads(n, n_species, seed, lo=700, hi=800):
     from ngspeciesid_b200.synth import simulate_reads
     rs = simulate_reads(n, n_species=n_species, len_lo=lo, len_hi=hi, seed=seed)
