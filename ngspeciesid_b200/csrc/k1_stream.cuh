@@ -65,7 +65,12 @@ K1S_DEV uint32_t k1s_bit(uint32_t key) { return k1s_fsr(0x80000000u, 0u, key); }
 
 // Table entry for (previous base, next 4 bases): kept bases left-aligned at bit 31, and 2 * count
 // in the low bits, so that   out = funnelshift_l(e, out, e)   appends them in one instruction.
-K1S_DEV uint32_t k1s_lut_entry(uint32_t idx)
+#ifdef K1S_HOST
+static inline
+#else
+__host__ __device__ inline
+#endif
+uint32_t k1s_lut_entry(uint32_t idx)
 {
     uint32_t prev = idx >> 8, byte = idx & 255u, bits = 0, cnt = 0;
     for (int t = 0; t < 4; ++t) {
@@ -312,6 +317,9 @@ __device__ __forceinline__ void k1s_sts16(uint32_t a, uint32_t v)
     asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v) : "memory");
 }
 
+// compression table, filled once per device by the host (ngsid_ctx_create); every block copies it
+__device__ uint32_t k1s_lut_dev[1024];
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K1S_THREADS)
 k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ woff,
@@ -325,7 +333,7 @@ k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict_
     uint32_t *regions = k1s_smem + 1024;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-    for (int idx = threadIdx.x; idx < 1024; idx += K1S_THREADS) lut[idx] = k1s_lut_entry((uint32_t)idx);
+    for (int idx = threadIdx.x; idx < 1024; idx += K1S_THREADS) lut[idx] = k1s_lut_dev[idx];
     __syncthreads();
 
     const int64_t r = (int64_t)blockIdx.x * K1S_THREADS + threadIdx.x;
@@ -342,17 +350,19 @@ k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict_
     const int nq = (nw + 3) >> 2;                 // 16-byte chunks
     const int nq_max = __reduce_max_sync(NGSID_FULL_MASK, nq);
     uint4 cur = (nq > 0) ? __ldg(pk) : make_uint4(0, 0, 0, 0);
+    uint4 nxt = (nq > 1) ? __ldg(pk + 1) : make_uint4(0, 0, 0, 0);
     K1SCompress C;
     k1s_compress_init(C, cur.x);
     for (int q = 0; q < nq_max; ++q) {
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (q + 1 < nq) nxt = __ldg(pk + q + 1);
+        uint4 nx2 = make_uint4(0, 0, 0, 0);                  // two loads in flight
+        if (q + 2 < nq) nx2 = __ldg(pk + q + 2);
         const int wb = 4 * q;
         k1s_compress_word(C, lut, cur.x, wb + 0 < nw, st, sw);
         k1s_compress_word(C, lut, cur.y, wb + 1 < nw, st, sw);
         k1s_compress_word(C, lut, cur.z, wb + 2 < nw, st, sw);
         k1s_compress_word(C, lut, cur.w, wb + 3 < nw, st, sw);
         cur = nxt;
+        nxt = nx2;
     }
     const int Lc = k1s_compress_finish(C, st, sw);        // -1: does not fit the region -> generic kernel
 

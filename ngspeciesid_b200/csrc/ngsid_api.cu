@@ -37,6 +37,12 @@ extern "C" int ngsid_ctx_create(int device_id, ngsid_ctx **out)
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j < 2; ++j)
             if (cudaEventCreate(&ctx->pev[i][j]) != cudaSuccess) { delete ctx; return NGSID_ECUDA; }
+    {
+        // K1 stream kernel: homopolymer-compression table (k1_stream.cuh), once per device
+        std::vector<uint32_t> lut(1024);
+        for (uint32_t i = 0; i < 1024; ++i) lut[i] = k1s_lut_entry(i);
+        if (cudaMemcpyToSymbol(k1s_lut_dev, lut.data(), 4096) != cudaSuccess) { delete ctx; return NGSID_ECUDA; }
+    }
     *out = ctx;
     return NGSID_OK;
 }
