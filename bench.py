@@ -346,8 +346,11 @@ def run_ours(args):
 
 
     # ---- consensus leg (BASELINE.json configs[2] shape): draft POA + racon-style polish of every
-    # cluster above the abundance cut-off, capped with the reference's own --max_seqs_for_consensus
-    if rank == 0 and world == 1 and not args.no_consensus:
+    # cluster above the abundance cut-off, capped with the reference's own --max_seqs_for_consensus.
+    # N > 1: clusters shard -- every rank polishes the clusters of its own batch (as they stand
+    # before the cross-batch merge rounds); no data-path collective, the aggregate is the sum of the
+    # bases over the slowest rank's time.
+    if not args.no_consensus:
         from ngspeciesid_b200.modules import consensus as C
         assign = state["assign"]
         rep = np.where(assign >= 0, assign, np.arange(n_mine))
@@ -366,24 +369,33 @@ def run_ours(args):
 
         l0 = eng.launch_count()
         consensus_step()
-        eng.sync()
+        barrier()
         tc = time.perf_counter()
         csteps = max(1, min(args.steps, 2))
         for _ in range(csteps):
             cons = consensus_step()
-        eng.sync()
+        barrier()
         dtc_ = (time.perf_counter() - tc) / csteps
-        result["consensus"] = {
-            "metric": "consensus bp/s (read bases consumed by draft POA + %d polish rounds / wall time)" % args.racon_iter,
-            "value": used_bases * (1 + args.racon_iter) / dtc_, "unit": "bp/s", "seconds_per_step": dtc_,
-            "clusters": len(lists), "reads_used": int(sum(len(l) for l in lists)),
-            "config": "clusters >= abundance_ratio %.3f x reads, --max_seqs_for_consensus %d, --racon_iter %d; host buffers in, "
-                      "consensus strings out" % (args.abundance_ratio, args.max_seqs, args.racon_iter),
-            "consensus_lengths": [len(c) for c in cons][:8], "gpu_launches": int(eng.launch_count() - l0)}
-        if not args.no_cpu and lists:
+        mine = {"bases": used_bases, "seconds": dtc_, "clusters": len(lists), "reads": int(sum(len(l) for l in lists)),
+                "launches": int(eng.launch_count() - l0)}
+        allc = [mine]
+        if world > 1:
+            allc = [None] * world
+            dist.all_gather_object(allc, mine)
+        if rank == 0:
+            dtc_ = max(x["seconds"] for x in allc)
+            result["consensus"] = {
+                "metric": "consensus bp/s (read bases consumed by draft POA + %d polish rounds / wall time)" % args.racon_iter,
+                "value": sum(x["bases"] for x in allc) * (1 + args.racon_iter) / dtc_, "unit": "bp/s", "seconds_per_step": dtc_,
+                "clusters": sum(x["clusters"] for x in allc), "reads_used": sum(x["reads"] for x in allc),
+                "config": "clusters >= abundance_ratio %.3f x reads, --max_seqs_for_consensus %d, --racon_iter %d; host buffers in, "
+                          "consensus strings out%s" % (args.abundance_ratio, args.max_seqs, args.racon_iter,
+                                                       "; clusters of each batch on its own GPU, max over ranks" if world > 1 else ""),
+                "consensus_lengths": [len(c) for c in cons][:8], "gpu_launches": sum(x["launches"] for x in allc)}
+        if rank == 0 and not args.no_cpu and lists:
             from oracle import consensus_oracle as co
             sample = lists[0][: args.cpu_consensus_reads]
-            recs = [(seq[offsets[i]:offsets[i + 1]].tobytes().decode(), qual[offsets[i]:offsets[i + 1]].tobytes().decode()) for i in sample]
+            recs = [(s_seq[s_off[i]:s_off[i + 1]].tobytes().decode(), s_qual[s_off[i]:s_off[i + 1]].tobytes().decode()) for i in sample]
             t3 = time.perf_counter()
             d0 = co.spoa_consensus(recs)
             p0 = co.racon_polish(d0, recs, args.racon_iter)

@@ -37,10 +37,21 @@ def draft_consensus_batch(eng, read_lists, max_nodes=0):
     return cons, nodes
 
 
-def _quality_prefix(eng):
-    if eng._qcs is None:
-        eng._qcs = np.concatenate([[0], np.cumsum(eng.h_qual.astype(np.int64) - 33)])
-    return eng._qcs
+def _quality_prefix(eng, reads):
+    """Prefix sums of (quality - 33) over the given uploaded reads only (a few thousand reads polish
+    a cluster; a prefix over the whole upload would cost more than the round itself).
+    Returns (prefix array, start of each read of `reads` in it)."""
+    reads = np.asarray(reads, dtype=np.int64)
+    uniq, inv = np.unique(reads, return_inverse=True)
+    lens = (eng.offsets[uniq + 1] - eng.offsets[uniq]).astype(np.int64)
+    starts = np.zeros(len(uniq) + 1, dtype=np.int64)
+    np.cumsum(lens, out=starts[1:])
+    # gather the quality bytes of the involved reads into one contiguous array
+    idx = np.repeat(eng.offsets[uniq].astype(np.int64) - starts[:-1], lens) + np.arange(starts[-1], dtype=np.int64)
+    q = eng.h_qual[idx].astype(np.int64) - 33
+    qcs = np.zeros(starts[-1] + 1, dtype=np.int64)
+    np.cumsum(q, out=qcs[1:])
+    return qcs, starts[:-1][inv]
 
 
 def polish_round_batch(eng, targets, read_lists, rc_lists=None, max_nodes=0):
@@ -73,8 +84,7 @@ def polish_round_batch(eng, targets, read_lists, rc_lists=None, max_nodes=0):
             A[idx[take]] = R[has][take]
     tlen = np.array([len(t) for t in targets], dtype=np.int64)
     tl = tlen[-B - 1]
-    qcs = _quality_prefix(eng)
-    roff = eng.offsets[A]
+    qcs, roff = _quality_prefix(eng, A)
     jobs, job_keys = [], []
     layer_rows = []
     n_pairs = len(A)
