@@ -408,6 +408,28 @@ def run_ours(args):
                 "sample": "first %d reads of the largest cluster, oracle/poa_oracle.cpp + consensus_oracle.py" % len(sample)}
             result["consensus"]["parity_sample_edit_distance"] = int(co.edit_distance(g_p, p0))
 
+    # ---- sort stage in front of the path (SURVEY.md 8 f rank 1): scores on the GPU, stable sort on the host
+    if rank == 0 and not args.no_consensus:
+        eng.sort_scores(K)
+        eng.sync()
+        ts = time.perf_counter()
+        for _ in range(3):
+            sc, er = eng.sort_scores(K)
+            srt_order = np.argsort(-sc, kind="stable")
+        dts = (time.perf_counter() - ts) / 3
+        result["sort_stage"] = {"metric": "reads/s scored + ordered (get_sorted_fastq_for_cluster arithmetic; reads resident, "
+                                          "scores D2H, stable argsort on the host)", "value": n_mine / dts, "unit": "reads/s",
+                                "ms": dts * 1e3, "reads": int(n_mine)}
+        if not args.no_cpu:
+            from oracle import cluster_oracle as oc
+            ns_ = min(n_mine, 2000)
+            t4 = time.perf_counter()
+            ref_sc = [oc.expected_error_free_kmers_score(s_qual[s_off[i]:s_off[i + 1]].tobytes().decode(), K) for i in range(ns_)]
+            dt4 = time.perf_counter() - t4
+            result["sort_stage"]["cpu_baseline"] = {"value": ns_ / dt4, "unit": "reads/s", "cores": 1, "kind": "port",
+                                                    "sample": "first %d reads, oracle/cluster_oracle.py" % ns_}
+            result["sort_stage"]["parity_sample_identical"] = bool(ref_sc == [float(x) for x in sc[:ns_]])
+
     # ---- K1 roofline on a replicated input far larger than L2 (rank 0 only)
     if rank == 0 and not args.no_roofline:
         rep = max(1, int(args.roofline_reads // max(1, n_mine)))

@@ -156,6 +156,17 @@ int ngsid_sg_align_paths(ngsid_ctx *ctx, const int32_t *a, const int32_t *b, con
                          int window, int32_t *out_score, int32_t *out_match, int32_t *out_cols,
                          int32_t *out_win);
 
+/* ---- sort stage (the step in front of the clustering path) --------------------------------
+ * Replaces the arithmetic of modules/get_sorted_fastq_for_cluster.py:23-33,140-152 for the uploaded
+ * reads: out_score[r] = (1 - E[erroneous k-mers] / n) * n, n = len - k + 1, computed with the
+ * reference's operation order in IEEE double (bit-identical), with phred_p_capped[c] =
+ * min(10^(-(c-33)/10), 0.79433); out_err_rate[r] = sum_c count(c) * phred_p_uncapped[c] / len
+ * (terms in ascending character order, Python's compensated sum). Filtering (len < 2k, compressed
+ * length < k, mean quality threshold), the stable descending sort and the score suffix of the
+ * read names stay on the host (ngspeciesid_b200/modules/get_sorted_fastq_for_cluster.py).      */
+int ngsid_sort_scores(ngsid_ctx *ctx, int k, const double *phred_p_capped, const double *phred_p_uncapped,
+                      double *out_score, double *out_err_rate);
+
 /* ---- K5: partial-order-alignment consensus ---------------------------------------------------
  * Replaces: the spoa call of consensus.run_spoa (modules/consensus.py:83-92: local alignment,
  * match 5, mismatch -4, linear gap -2, quality weights, heaviest-bundle consensus) and the

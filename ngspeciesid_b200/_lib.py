@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libngsid.so")
 EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last_error",
            "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
-           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus"]
+           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus"]
 
 
 class ClusterParams(ctypes.Structure):
@@ -72,6 +72,7 @@ def load():
     lib.ngsid_get_minimizers.argtypes = [vp, i64, i64, vp, vp, vp, vp, i64, P(i64)]
     lib.ngsid_quality_stats.argtypes = [vp, vp, vp]
     lib.ngsid_get_quality_stats.argtypes = [vp, i64, i64, vp, vp, vp]
+    lib.ngsid_sort_scores.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ngsid_cluster.argtypes = [vp, P(ClusterParams), vp, i64, vp, i64, vp, vp, vp, P(ClusterStats)]
     lib.ngsid_sg_block_align.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.ngsid_sg_align_paths.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp]

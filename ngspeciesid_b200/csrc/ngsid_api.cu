@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "ngsid_internal.cuh"
 #include "k1_minimizers.cuh"
+#include "k0_sortscore.cuh"
 #include "k1_stream.cuh"
 #include "k2_map.cuh"
 #include "k4_align.cuh"
@@ -87,7 +88,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
                       &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
-                      &ctx->d_newslots, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+                      &ctx->d_newslots, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
     cudaEventDestroy(ctx->ev0);
@@ -354,6 +355,41 @@ extern "C" int ngsid_quality_stats(ngsid_ctx *ctx, const double *phred_p, const 
         KERNEL_CHECK(ctx);
     }
     ctx->have_q = true;
+    return NGSID_OK;
+}
+
+// ================================================================================ sort stage (row f.1)
+extern "C" int ngsid_sort_scores(ngsid_ctx *ctx, int k, const double *phred_p_capped, const double *phred_p_uncapped,
+                                 double *out_score, double *out_err_rate)
+{
+    if (!ctx || !phred_p_capped || !phred_p_uncapped || !out_score || !out_err_rate) return NGSID_EINVAL;
+    if (k < 1 || k > 64) return fail(ctx, NGSID_EINVAL, "k out of range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = ctx->n_reads;
+    if (n == 0) return NGSID_OK;
+    CUDA_TRY(ctx, ctx->d_ss_tab.ensure(2 * 128 * sizeof(double) + 16 * sizeof(double)));
+    CUDA_TRY(ctx, ctx->d_ss_score.ensure((n + 1) * sizeof(double)));
+    CUDA_TRY(ctx, ctx->d_ss_err.ensure(2 * (n + 1) * sizeof(double) + n + 64));
+    double *tab = ctx->d_ss_tab.as<double>();
+    double thr[14];
+    for (int t = 0; t < 14; ++t) thr[t] = 1e300;          // buckets are not used here
+    CUDA_TRY(ctx, cudaMemcpyAsync(tab, phred_p_capped, 128 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tab + 128, phred_p_uncapped, 128 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(tab + 256, thr, sizeof thr, cudaMemcpyHostToDevice, ctx->stream));
+    k0s_sortscore_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(
+        ctx->d_qual.as<uint8_t>(), ctx->d_off.as<int64_t>(), tab, k, ctx->d_ss_score.as<double>(), n);
+    KERNEL_CHECK(ctx);
+    // mean error probability over the raw qualities with the uncapped table
+    // (get_sorted_fastq_for_cluster.py:145-146): the histogram + compensated sum of K0
+    double *erru = ctx->d_ss_err.as<double>(), *errc = erru + (n + 1);
+    uint8_t *bucket = reinterpret_cast<uint8_t *>(errc + (n + 1));
+    int blocks = (int)std::min<int64_t>((n + 7) / 8, (int64_t)ctx->sm_count * 8);
+    k0_quality_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_qual.as<uint8_t>(),
+                                                       ctx->d_off.as<int64_t>(), tab + 128, tab + 256, errc, erru, bucket, n);
+    KERNEL_CHECK(ctx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_score, ctx->d_ss_score.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out_err_rate, erru, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return NGSID_OK;
 }
 

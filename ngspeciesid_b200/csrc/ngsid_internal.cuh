@@ -67,6 +67,7 @@ struct ngsid_ctx {
     // ---- K0 results
     bool have_q = false;
     DevBuf d_errc, d_erru, d_bucket, d_phred, d_thr;
+    DevBuf d_ss_tab, d_ss_score, d_ss_err;       // sort-stage scores (row f.1)
 
     // ---- clustering scratch (see cluster_driver.cuh)
     DevBuf d_keys, d_heads, d_nodes, d_cursor, d_slot_read, d_slot_pos, d_slot_state;

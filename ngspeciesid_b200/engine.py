@@ -13,6 +13,8 @@ from ._lib import ClusterParams, ClusterStats, NgsidError, PoaParams, as_array, 
 
 # PHRED char -> capped error probability, exactly the reference's table (modules/cluster.py:233)
 PHRED_P = np.array([min(10 ** (-(c - 33) / 10.0), 0.79433) for c in range(128)], dtype=np.float64)
+# uncapped table of the sort stage (modules/get_sorted_fastq_for_cluster.py:21)
+PHRED_P_UNCAPPED = np.array([10 ** (-(c - 33) / 10.0) for c in range(128)], dtype=np.float64)
 
 
 def bucket_thresholds():
@@ -152,6 +154,15 @@ class Engine(object):
         thr = bucket_thresholds()
         self._check(self.lib.ngsid_quality_stats(self.h, ptr(PHRED_P), ptr(thr)))
         self._q_done = True
+
+    def sort_scores(self, k):
+        """Sort-stage keys of the uploaded reads (get_sorted_fastq_for_cluster.py:23-33,145-152):
+        (score, mean error probability with the uncapped table), both float64, bit-identical to the
+        reference's arithmetic."""
+        score, err = np.zeros(self.n_reads), np.zeros(self.n_reads)
+        if self.n_reads:
+            self._check(self.lib.ngsid_sort_scores(self.h, k, ptr(PHRED_P), ptr(PHRED_P_UNCAPPED), ptr(score), ptr(err)))
+        return score, err
 
     def get_quality_stats(self, begin=0, end=None):
         end = self.n_reads if end is None else end

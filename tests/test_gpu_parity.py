@@ -378,3 +378,56 @@ def test_k1_properties_at_scale(eng):
         exp = oc.minimizers(sc, k, w)
         got = [(decode_kmer(kmer[j], k), int(pos[j])) for j in range(starts[i], starts[i + 1])]
         assert got == exp
+
+
+# ---------------------------------------------------------------- sort stage (SURVEY.md 8 f, rank 1)
+@pytest.mark.parametrize("tag", ["h1_t1", "supp1k_t1", "synth2k_t1", "synthpb_t1"])
+def test_sort_stage_matches_reference_golden(eng, tag):
+    """Scores (as the reference prints them), kept reads and their order against the vectors the
+    reference itself produced, and against the oracle's restatement including the error rates."""
+    from ngspeciesid_b200.modules import get_sorted_fastq_for_cluster as S
+    g = load_golden("clusters_%s.json.gz" % tag)
+    args = scenario_args(g)
+    recs = scenario_reads(tag)
+    read_array, error_rates = S.score_records(recs, args.k, 7.0, eng)
+    names = [r[0] for r in recs]
+    assert [r[0] for r in read_array] == [names[i] for i in g["sorted_input_index"]]
+    assert ["{0}".format(r[3]) for r in read_array] == g["sorted_scores"]
+    exp = oc.sort_stage(recs, args.k)
+    assert [(a + "_{0}".format(s), q1, q2, s) for a, q1, q2, s in read_array] == exp
+    # error rates of the kept reads, file order (the reference sorts them afterwards)
+    kept = sorted(g["sorted_input_index"])
+    exp_e = [oc.poisson_mean(recs[i][2], oc.PHRED_P_UNCAPPED) / float(len(recs[i][2])) for i in kept]
+    assert error_rates == exp_e
+
+
+def test_sort_stage_filters_and_file(eng, tmp_path):
+    """Short / degenerate / low-quality reads are skipped exactly like the reference does, ties keep
+    file order, and main() writes the reference's sorted.fastq and logfile."""
+    import argparse
+    from ngspeciesid_b200.modules import get_sorted_fastq_for_cluster as S
+    rng = np.random.default_rng(17)
+    recs = []
+    for i in range(300):
+        n = int(rng.integers(5, 120))
+        s = "".join(rng.choice(list("ACGT"), size=n))
+        if i % 17 == 0:
+            s = "A" * n                                          # compresses to one base
+        q = "".join(chr(33 + int(x)) for x in rng.integers(2 if i % 5 else 1, 45 if i % 7 else 9, size=n))
+        recs.append(("r%d extra" % i, s, q))
+    recs += [("dupA", recs[3][1], recs[3][2]), ("dupB", recs[3][1], recs[3][2])]     # equal scores: stable
+    for k in (13, 15, 7):
+        ra, er = S.score_records(recs, k, 7.0, eng)
+        exp = oc.sort_stage(recs, k)
+        assert [(a + "_{0}".format(s), x, y, s) for a, x, y, s in ra] == exp
+    fq = tmp_path / "in.fastq"
+    with open(fq, "w") as f:
+        for a, s, q in recs:
+            f.write("@%s\n%s\n+\n%s\n" % (a, s, q))
+    args = argparse.Namespace(fastq=str(fq), outfolder=str(tmp_path), outfile=str(tmp_path / "sorted.fastq"), k=13,
+                              quality_threshold=7.0, nr_cores=1, use_old_sorted_file=False)
+    # the shared engine of modules/ is used by main()
+    out = S.main(args)
+    exp = oc.sort_stage(recs, 13)
+    assert open(out).read() == "".join("@{0}\n{1}\n+\n{2}\n".format(a, s, q) for a, s, q, _ in exp)
+    assert open(tmp_path / "logfile.txt").read().startswith("Lowest read error rate:")
