@@ -1051,17 +1051,28 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
         rc = R.insert_slots(slot0, (int)U.size());
         if (rc) return cleanup(rc);
 
-        // ---- phase 2: resolve the tentative ones in order against the certain ones before them
-        for (size_t u = 1; u < U.size(); ++u) {
-            k2_iota_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_list.as<int32_t>(), U[u], 1);
-            KERNEL_CHECK(ctx);
-            rc = R.run_map(ctx->d_list.as<int32_t>(), 1);
+        // ---- phase 2: resolve the tentative ones in order against the certain ones before them.
+        // All unresolved ones are mapped in one batch against the representatives that are certain
+        // so far. The decision of the first of them is final; as long as a resolved one turns out
+        // not to be a representative the certain set is unchanged, so the next decision of the batch
+        // is final too. The batch ends at the first one that IS a representative (the certain set
+        // grew: the rest is mapped again). Batches = new representatives in the tile, not tentatives.
+        for (size_t u = 1; u < U.size();) {
+            h_list.assign(U.begin() + u, U.end());
+            CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_list.p, h_list.data(), h_list.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            rc = R.run_map(ctx->d_list.as<int32_t>(), (int)h_list.size());
             if (rc) return cleanup(rc);
-            rc = R.fetch_dec(U[u], U[u] + 1);
+            rc = R.fetch_dec(U[u], U.back() + 1);
             if (rc) return cleanup(rc);
             R.st.n_chain_steps++;
-            rc = R.set_state(slot0 + (int)u, R.h_dec[U[u]] == DEC_NEW ? SLOT_VALID : SLOT_DEAD);
-            if (rc) return cleanup(rc);
+            while (u < U.size()) {
+                const bool is_new = R.h_dec[U[u]] == DEC_NEW;
+                rc = R.set_state(slot0 + (int)u, is_new ? SLOT_VALID : SLOT_DEAD);
+                if (rc) return cleanup(rc);
+                ++u;
+                if (is_new) break;
+            }
         }
 
         // ---- phase 3: the other reads after the first new representative see the new ones
