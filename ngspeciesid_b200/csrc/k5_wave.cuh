@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
                 }
                 if (tid == 0) {
                     if (G.err == 0 && (!fits || s_D != 0)) poa_topo_sort(G);   // global-memory fallback
-                    cyc_add += clock64() - t4;
+                    cyc_cons += clock64() - t4;                                // reported with the consensus slot
                 }
                 __syncthreads();
             }
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
             int len = -1;
             const long long t3 = clock64();
             if (G.err == 0) len = poa_consensus(G, A.trim, A.out + (size_t)job * A.out_stride, (int)A.out_stride);
-            cyc_cons = clock64() - t3;
+            cyc_cons += clock64() - t3;
             if (A.cycles) { A.cycles[job * 4] = cyc_dp; A.cycles[job * 4 + 1] = cyc_tb; A.cycles[job * 4 + 2] = cyc_add; A.cycles[job * 4 + 3] = cyc_cons; }
             A.out_len[job] = len;
             if (A.out_nodes) A.out_nodes[job] = G.V;
