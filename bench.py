@@ -449,8 +449,17 @@ def run_ours(args):
         except Exception:
             pass
         achieved = alg_bytes / (ms / 1000.0) / 1e9
+        # DRAM traffic of one launch from the committed ncu --set full capture (same command, same size)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
+            if int(tj["reads_per_launch"]) == len(blens):
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"]); traffic_src = tj["source"]
+        except Exception:
+            pass
         result["roofline"] = {"kernel": "k1_stream_kernel (thread per read: compress + window minima; warp per 32 reads: output)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                              "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                              "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                              "algorithmic_bytes_per_launch": int(alg_bytes), "bound_note": "reported against HBM as BASELINE asks; the kernel is ALU-issue bound (DESIGN.md 4.0/4.1)",
                               "reads_per_launch": int(len(blens)), "bytes_per_read": alg_bytes / len(blens),
                               "kernel_ms": ms, "reads_per_s": len(blens) / (ms / 1000.0)}
         eng.upload(h_seq, h_qual, h_off)

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
             int bestv = 0, besti = 0, bestj = 0;
             int sinkv = POA_NEG, sinki = 0x7fffffff;            // global mode: best sink row at column L
             const int r_begin = tid * RPT, r_end = min(V, r_begin + RPT);
-            const int n_steps = L + 1 + K5W_THREADS - 1;
+            const int n_steps = L + 1 + (V + RPT - 1) / RPT - 1;      // the last thread that owns rows finishes column L
             const int dmask = D - 1;
             // hot loop: 32-bit shared-window addresses, running pointers per row
             const uint32_t s_hist = (uint32_t)__cvta_generic_to_shared(hist);
