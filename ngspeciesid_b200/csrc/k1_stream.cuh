@@ -333,24 +333,25 @@ k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict_
     uint32_t *regions = k1s_smem + 1024;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-    for (int idx = threadIdx.x; idx < 1024; idx += K1S_THREADS) lut[idx] = k1s_lut_dev[idx];
-    __syncthreads();
-
+    // per-read metadata and the first two 16-byte chunks are requested before the table copy and
+    // its barrier, so that their latency overlaps
     const int64_t r = (int64_t)blockIdx.x * K1S_THREADS + threadIdx.x;
     const bool have = r < n_reads;
     const int L = have ? (int)(off[r + 1] - off[r]) : 0;
     const uint4 *pk = reinterpret_cast<const uint4 *>(packed + (have ? woff[r] : 0));
     const int64_t my_moff = have ? moff[r] : 0;
+    const int nw = (L + 15) >> 4;                 // raw words of this read
+    const int nq = (nw + 3) >> 2;                 // 16-byte chunks
+    uint4 cur = (nq > 0) ? __ldg(pk) : make_uint4(0, 0, 0, 0);
+    uint4 nxt = (nq > 1) ? __ldg(pk + 1) : make_uint4(0, 0, 0, 0);
+    for (int idx = threadIdx.x; idx < 1024; idx += K1S_THREADS) lut[idx] = k1s_lut_dev[idx];
+    __syncthreads();
     uint32_t *st = regions + (size_t)threadIdx.x * rs;
     uint32_t *bm = st + sw;
     const uint32_t topmask = ~((1u << (32 - 2 * k)) - 1u);
 
     // ---- phase A: compression. 64 bases (one 16-byte load) per iteration, next load in flight.
-    const int nw = (L + 15) >> 4;                 // raw words of this read
-    const int nq = (nw + 3) >> 2;                 // 16-byte chunks
     const int nq_max = __reduce_max_sync(NGSID_FULL_MASK, nq);
-    uint4 cur = (nq > 0) ? __ldg(pk) : make_uint4(0, 0, 0, 0);
-    uint4 nxt = (nq > 1) ? __ldg(pk + 1) : make_uint4(0, 0, 0, 0);
     K1SCompress C;
     k1s_compress_init(C, cur.x);
     for (int q = 0; q < nq_max; ++q) {
@@ -391,46 +392,58 @@ k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict_
     const uint32_t s_tbl = s_rstart + 4u * (K1S_GROUP + 2);                          // 8-byte aligned
     const uint32_t bm_off = (uint32_t)sw * 4u;
     const int kshift = 32 - 2 * k;
-    const int dq = 32 / n_it, dc = 32 % n_it;
-    const int q0 = lane / n_it, c0 = lane % n_it;
+    // extraction: two consecutive bitmap words per lane and pass (two independent extraction
+    // chains per lane, one scan per 64 words)
+    const int dq = 64 / n_it, dc = 64 % n_it;
+    const int q0 = (2 * lane) / n_it, c0 = (2 * lane) % n_it;
     const int total_items = K1S_GROUP * n_it;
     uint32_t my_n = 0;
     bool my_slow = have && !ok;
     for (int g0 = 0; g0 < 32; g0 += K1S_GROUP) {
         if (!__any_sync(NGSID_FULL_MASK, have && lane >= g0)) break;
-        int q = q0, c = c0;
+        int qa = q0, ca = c0;
         uint32_t run = 0;
-        for (int f0 = 0; f0 < total_items; f0 += 32) {
-            const bool valid = f0 + lane < total_items;
-            uint32_t m = 0;
-            if (valid) m = k1s_lds32(s_wreg + (uint32_t)(g0 + q) * rsb + bm_off + 4u * (uint32_t)c);
-            const uint32_t n = (uint32_t)__popc(m);
+        for (int f0 = 0; f0 < total_items; f0 += 64) {
+            const int fa = f0 + 2 * lane;
+            const bool va = fa < total_items, vb = fa + 1 < total_items;
+            int qb = qa, cb = ca + 1;
+            if (cb >= n_it) { cb = 0; ++qb; }
+            uint32_t ma = 0, mb = 0;
+            if (va) ma = k1s_lds32(s_wreg + (uint32_t)(g0 + qa) * rsb + bm_off + 4u * (uint32_t)ca);
+            if (vb) mb = k1s_lds32(s_wreg + (uint32_t)(g0 + qb) * rsb + bm_off + 4u * (uint32_t)cb);
+            const uint32_t na = (uint32_t)__popc(ma), n = na + (uint32_t)__popc(mb);
             uint32_t incl = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t v = __shfl_up_sync(NGSID_FULL_MASK, incl, d);
                 if (lane >= d) incl += v;
             }
-            const uint32_t o = run + incl - n;
-            if (valid && c == 0) k1s_sts32(s_rstart + 4u * (uint32_t)q, o);
+            const uint32_t oa = run + incl - n, ob = oa + na;
+            if (va && ca == 0) k1s_sts32(s_rstart + 4u * (uint32_t)qa, oa);
+            if (vb && cb == 0) k1s_sts32(s_rstart + 4u * (uint32_t)qb, ob);
             run += __shfl_sync(NGSID_FULL_MASK, incl, 31);
-            if (o + n > (uint32_t)scap) m = 0;               // group overflow: its reads go to the slow list
-            uint32_t sa = s_stage + 2u * o;
-            const uint32_t pb = ((uint32_t)q << 13) | ((uint32_t)c << 5);     // read-in-group | position
+            if (oa + n > (uint32_t)scap) { ma = 0; mb = 0; }   // group overflow: its reads go to the slow list
+            uint32_t sa = s_stage + 2u * oa, sb = s_stage + 2u * ob;
+            const uint32_t pa = ((uint32_t)qa << 13) | ((uint32_t)ca << 5);   // read-in-group | position
+            const uint32_t pb = ((uint32_t)qb << 13) | ((uint32_t)cb << 5);
 #pragma unroll
             for (int s = 0; s < K1S_SLOTS; ++s) {
-                const uint32_t p = k1s_clz(m);
-                if (m != 0u) k1s_sts16(sa + 2u * s, pb + p);
-                m &= k1s_fsr(0x7fffffffu, 0u, p);           // clears bit 31 - p (the bits above it are 0)
+                const uint32_t xa = k1s_clz(ma), xb = k1s_clz(mb);
+                if (ma != 0u) k1s_sts16(sa + 2u * s, pa + xa);
+                if (mb != 0u) k1s_sts16(sb + 2u * s, pb + xb);
+                ma &= k1s_fsr(0x7fffffffu, 0u, xa);         // clears bit 31 - x (the bits above it are 0)
+                mb &= k1s_fsr(0x7fffffffu, 0u, xb);
             }
-            sa += 2u * K1S_SLOTS;
-            while (__any_sync(NGSID_FULL_MASK, m != 0u)) {
-                const uint32_t p = k1s_clz(m);
-                if (m != 0u) { k1s_sts16(sa, pb + p); sa += 2u; }
-                m &= k1s_fsr(0x7fffffffu, 0u, p);
+            sa += 2u * K1S_SLOTS; sb += 2u * K1S_SLOTS;
+            while (__any_sync(NGSID_FULL_MASK, (ma | mb) != 0u)) {
+                const uint32_t xa = k1s_clz(ma), xb = k1s_clz(mb);
+                if (ma != 0u) { k1s_sts16(sa, pa + xa); sa += 2u; }
+                if (mb != 0u) { k1s_sts16(sb, pb + xb); sb += 2u; }
+                ma &= k1s_fsr(0x7fffffffu, 0u, xa);
+                mb &= k1s_fsr(0x7fffffffu, 0u, xb);
             }
-            c += dc; q += dq;
-            if (c >= n_it) { c -= n_it; ++q; }
+            ca += dc; qa += dq;
+            if (ca >= n_it) { ca -= n_it; ++qa; }
         }
         if (lane == 0) k1s_sts32(s_rstart + 4u * K1S_GROUP, run);
         __syncwarp();
