@@ -677,7 +677,8 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         K5WArgs Wa;
         Wa.a = A;
         Wa.dir = ctx->d_poa_dir.as<uint8_t>(); Wa.dir_bytes = dir_bytes;
-        const size_t wave_smem = 200 * 1024;
+        size_t wave_smem = 200 * 1024;
+        if (const char *e = getenv("NGSID_K5W_SMEM_KB")) wave_smem = std::min<size_t>(wave_smem, (size_t)std::max(8, atoi(e)) * 1024);   // tests: force the fallback
         Wa.smem_words = (int)(wave_smem / 4);
         CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
         k5w_poa_kernel<<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);

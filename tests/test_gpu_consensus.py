@@ -152,3 +152,20 @@ def test_highest_aln_identity(eng):
     cents = [[10, 1, a, "p1"], [8, 2, co.revcomp(b), "p2"], [5, 3, "".join(rng.choice(list("ACGT"), size=600)), "p3"]]
     out = C.detect_reverse_complements(cents, 0.9)
     assert [c[:2] for c in out] == [[18, 1], [5, 3]] and out[0][3] == ["p1", "p2"]
+
+
+def test_wavefront_falls_back_to_row_kernel(eng, poa_shape, monkeypatch):
+    """A graph that outgrows the wavefront kernel's shared-memory ring must be finished by the row
+    kernel with the same result (the ring is made tiny here)."""
+    if poa_shape != "wave":
+        pytest.skip("fallback only exists for the wavefront shape")
+    from ngspeciesid_b200.modules import consensus as C
+    rs, groups, _tpl = species_reads(120, 1, 43, 500, 560)
+    recs = [rs.read(i) for i in range(len(rs))]
+    eng.upload_records(recs)
+    lst = [i for i in range(len(rs)) if rs.strand[i] == 0][:20]
+    exp = co.spoa_consensus([recs[i] for i in lst])
+    monkeypatch.setenv("NGSID_K5W_SMEM_KB", "16")
+    got, nodes = C.draft_consensus_batch(eng, [lst, lst[:5]])
+    assert got[0] == exp and got[1] == co.spoa_consensus([recs[i] for i in lst[:5]])
+    assert int(nodes[0]) > 500
