@@ -7,10 +7,10 @@
 // 0.5 byte/cell of trace that goes to HBM/L2 in fully coalesced 128-byte rows (one row per
 // wavefront step and strip of 256 rows).
 //
-// Trace nibble of cell (i,j):  bit 0: the horizontal gap state D beats the diagonal; bit 1: the
-// vertical gap state I beats max(diagonal, D)  (source of H = I if bit 1, else D if bit 0, else the
-// diagonal; the traceback re-reads the two bases to tell match from mismatch); bit 2: D opened
-// from H; bit 3: I opened from H.
+// Trace nibble of cell (i,j):  bit 0 (a): H is not the diagonal; bit 1 (b): H is not the
+// horizontal gap state D  (source of H = diagonal if !a, else D if !b, else the vertical gap state
+// I -- the oracle's tie order; the traceback re-reads the two bases to tell match from mismatch);
+// bit 2: D opened from H; bit 3: I opened from H.
 // Word layout: trace[slot][pass][step t][lane] holds rows 8*lane..8*lane+7 of column j = t - lane.
 //
 // The DP kernel has two shapes. MULTI = false: one warp per pair, the strips of 256 rows ("passes")
@@ -48,20 +48,22 @@ struct K4TSeqs {
 };
 
 // One cell. H/D are the lane's row state, (uH, uI) come from the row above, dH is the diagonal.
-// Every comparison is a VIMNMX with predicate output; the trace bits are predicated ORs.
+// Written for the ALU pipe (half rate for compare / select / min-max, full rate for plain adds):
+// fused add-max for the two gap states, one 3-input maximum for H, and every trace bit is ONE
+// compare (result != the operand that loses ties) plus one predicated add into the trace word.
 #define K4T_CELL(r)                                                                   \
     {                                                                                 \
-        bool pI, pD, p1, p2;                                                          \
-        const int vI = __vibmax_s32(uI - 1, uH - open, &pI);      /* pI: extend >= open */ \
-        const int vD = __vibmax_s32(D[r] - 1, H[r] - open, &pD);                      \
+        const int ie = uI - 1;                                                        \
+        const int vI = __viaddmax_s32(uH, nopen, ie);             /* max(uH - open, uI - 1) */ \
+        const int dext = D[r] - 1;                                                    \
+        const int vD = __viaddmax_s32(H[r], nopen, dext);                             \
         int hd = dH + 2;                                                              \
         if (c1[r] != c2) hd = dH - 2;                                                 \
-        const int h1 = __vibmax_s32(hd, vD, &p1);                 /* p1: diagonal >= D */ \
-        const int h = __vibmax_s32(h1, vI, &p2);                  /* p2: max(diag, D) >= I */ \
-        if (!p1) word |= 1u << (4 * r);                                               \
-        if (!p2) word |= 2u << (4 * r);                                               \
-        if (!pD) word |= 4u << (4 * r);                                               \
-        if (!pI) word |= 8u << (4 * r);                                               \
+        const int h = __vimax3_s32(hd, vD, vI);                                       \
+        if (h != hd) word += 1u << (4 * r);                       /* a: H is not the diagonal */ \
+        if (h != vD) word += 2u << (4 * r);                       /* b: H is not D */ \
+        if (vD != dext) word += 4u << (4 * r);                    /* D opened from H (open > extend) */ \
+        if (vI != ie) word += 8u << (4 * r);                      /* I opened from H */ \
         dH = H[r];                                                                    \
         H[r] = h; D[r] = vD;                                                          \
         uH = h; uI = vI;                                                              \
@@ -91,6 +93,7 @@ k4t_dp_kernel(K4TSeqs Q,
         const int64_t pr = pair0 + sl;
         const int ra = pa[pr * stride], rb = pb[pr * stride];
         const int open = popen[pr * stride];
+        const int nopen = -open;
         const uint8_t *s1 = Q.ptr(ra);
         const uint8_t *s2 = Q.ptr(rb);
         const int n1 = Q.len(ra);
@@ -321,7 +324,7 @@ k4t_traceback_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
             const uint32_t word = ring[(t & (K4T_RING - 1)) * 32 + strip];
             const uint32_t nib = (word >> (4 * (i & 7))) & 15u;
             if (state == 0) {
-                if (nib & 2u) state = 3;
+                if ((nib & 3u) == 3u) state = 3;
                 else if (nib & 1u) state = 2;
                 else {
                     const uint32_t mt = (q1[i] == q2[j]) ? 1u : 0u;
