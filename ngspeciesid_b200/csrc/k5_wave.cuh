@@ -39,6 +39,12 @@ struct K5WArgs {
     int smem_words;          // dynamic shared memory available for hist + meta (32-bit words)
 };
 
+__device__ __forceinline__ uint32_t k5w_opaque(uint32_t v)
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 __device__ __forceinline__ uint4 k5w_lds128(uint32_t a)
 {
     uint4 v;
@@ -149,9 +155,11 @@ __global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
             const int n_steps = L + 1 + (V + RPT - 1) / RPT - 1;      // the last thread that owns rows finishes column L
             const int dmask = D - 1;
             // hot loop: 32-bit shared-window addresses, running pointers per row
-            const uint32_t s_hist = (uint32_t)__cvta_generic_to_shared(hist);
-            const uint32_t s_meta = (uint32_t)__cvta_generic_to_shared(smeta);
-            const uint32_t row_b = 4u * (uint32_t)DS;            // bytes per ring row
+            // (made opaque: otherwise the compiler rebuilds the shared-window base from the CTA id
+            // next to every access instead of keeping it in a register)
+            const uint32_t s_hist = k5w_opaque((uint32_t)__cvta_generic_to_shared(hist));
+            const uint32_t s_meta = k5w_opaque((uint32_t)__cvta_generic_to_shared(smeta));
+            const uint32_t row_b = k5w_opaque(4u * (uint32_t)DS);            // bytes per ring row
             const uint32_t a_virt = s_hist + (uint32_t)(V + tid) * row_b;
             for (int st = 0; st < n_steps; ++st) {
                 const int j = st - tid;
