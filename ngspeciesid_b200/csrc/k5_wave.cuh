@@ -52,7 +52,8 @@ __device__ __forceinline__ uint4 k5w_lds128(uint32_t a)
     return v;
 }
 
-__global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
+template <int MODE>
+__global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
 {
     const K5Args &A = W.a;
     __shared__ PoaGraph G;
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
                 continue;
             }
             if (tid == 0) t0 = clock64();
-            const int g = A.g, mode = A.mode;
+            const int g = A.g;
+            constexpr int mode = MODE;                          // 0 local (draft), 1 global (polishing windows)
             const size_t ld = (size_t)L + 1;
             const int RPT = ((V + K5W_THREADS - 1) / K5W_THREADS) | 1;      // odd: lanes of a warp hit distinct banks
             // ring rows: V graph rows | one virtual-source row per thread | one row of -infinity.
@@ -241,8 +243,10 @@ __global__ void __launch_bounds__(K5W_THREADS) k5w_poa_kernel(K5WArgs W)
                         DIR[goff] = (uint8_t)bdir;
                         if (mode) {
                             if (j == L && (m.x & 0x40000u) && h > sinkv) { sinkv = h; sinki = r + 1; }
-                        } else if (h > bestv || (h == bestv && h > 0 && (r + 1 < besti || (r + 1 == besti && j < bestj)))) {
-                            bestv = h; besti = r + 1; bestj = j;
+                        } else if (h >= bestv) {                 // rare: only cells on or next to the best path
+                            if (h > bestv || (h > 0 && (r + 1 < besti || (r + 1 == besti && j < bestj)))) {
+                                bestv = h; besti = r + 1; bestj = j;
+                            }
                         }
                     }
                 }

@@ -680,8 +680,13 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         size_t wave_smem = 200 * 1024;
         if (const char *e = getenv("NGSID_K5W_SMEM_KB")) wave_smem = std::min<size_t>(wave_smem, (size_t)std::max(8, atoi(e)) * 1024);   // tests: force the fallback
         Wa.smem_words = (int)(wave_smem / 4);
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
-        k5w_poa_kernel<<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);
+        if (params->mode) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
+            k5w_poa_kernel<1><<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);
+        } else {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
+            k5w_poa_kernel<0><<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);
+        }
         KERNEL_CHECK(ctx);
         CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
