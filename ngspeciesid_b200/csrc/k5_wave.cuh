@@ -45,6 +45,13 @@ __device__ __forceinline__ uint32_t k5w_opaque(uint32_t v)
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
     return r;
 }
+template <class T>
+__device__ __forceinline__ T *k5w_opaque_ptr(T *p)
+{
+    unsigned long long v = (unsigned long long)p, r;
+    asm volatile("mov.u64 %0, %1;" : "=l"(r) : "l"(v));
+    return (T *)r;
+}
 __device__ __forceinline__ uint4 k5w_lds128(uint32_t a)
 {
     uint4 v;
@@ -163,19 +170,27 @@ __global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
             const uint32_t s_meta = k5w_opaque((uint32_t)__cvta_generic_to_shared(smeta));
             const uint32_t row_b = k5w_opaque(4u * (uint32_t)DS);            // bytes per ring row
             const uint32_t a_virt = s_hist + (uint32_t)(V + tid) * row_b;
+            // scoring constants and output bases in registers for the whole layer (otherwise every
+            // cell re-reads them from the constant bank and rebuilds the slot bases from blockIdx)
+            const int sc_m = (int)k5w_opaque((uint32_t)A.m), sc_x = (int)k5w_opaque((uint32_t)A.x);
+            const int gq = (int)k5w_opaque((uint32_t)g);
+            uint8_t *const DIRq = k5w_opaque_ptr(DIR);
+            int32_t *const Hq = k5w_opaque_ptr(H);
             for (int st = 0; st < n_steps; ++st) {
                 const int j = st - tid;
                 if (j >= 0 && j <= L && r_begin < r_end) {
                     const uint32_t cj = (j >= 1) ? sseq[j - 1] : 0xffffu;
                     const uint32_t so = 4u * (uint32_t)(j & dmask), so1 = 4u * (uint32_t)((j - 1) & dmask);
-                    k1s_sts32(a_virt + so, (uint32_t)(mode ? j * g : 0));          // virtual row 0, column j
+                    k1s_sts32(a_virt + so, (uint32_t)(mode ? j * gq : 0));          // virtual row 0, column j
                     uint32_t a_hist = s_hist + (uint32_t)r_begin * row_b;
                     uint32_t a_meta = s_meta + 32u * (uint32_t)r_begin;
-                    size_t goff = (size_t)(r_begin + 1) * ld + (size_t)j;
-                    for (int r = r_begin; r < r_end; ++r, a_hist += row_b, a_meta += 32u, goff += ld) {
+                    const size_t goff0 = (size_t)(r_begin + 1) * ld + (size_t)j;
+                    uint8_t *dirp = DIRq + goff0;
+                    int32_t *hout = Hq + goff0;
+                    for (int r = r_begin; r < r_end; ++r, a_hist += row_b, a_meta += 32u, dirp += ld, hout += ld) {
                         const uint4 m = k5w_lds128(a_meta);
                         const int np = (int)((m.x >> 8) & 255u);
-                        const int sc = ((m.x & 255u) == cj) ? A.m : A.x;
+                        const int sc = ((m.x & 255u) == cj) ? sc_m : sc_x;
                         int best = POA_NEG, bdir = K5W_STOP;
                         int bup = POA_NEG, udir = 0;
                         // in-edge u of this row: values of the predecessor row at columns j-1 and j
@@ -186,7 +201,7 @@ __global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
                                 const uint32_t hp = s_hist + (idx) * row_b;                         \
                                 pa = (int)k1s_lds32(hp + so1); pb = (int)k1s_lds32(hp + so);        \
                             } else {                                                                \
-                                const int32_t *hp = H + (size_t)prank[(size_t)r * K5W_FAST + (u)] * ld + j; \
+                                const int32_t *hp = Hq + (size_t)prank[(size_t)r * K5W_FAST + (u)] * ld + j; \
                                 pa = (j >= 1) ? hp[-1] : POA_NEG;                                   \
                                 pb = hp[0];                                                         \
                             }                                                                       \
@@ -230,17 +245,17 @@ __global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
                         int h;
                         if (j >= 1) {
                             h = best + sc;                                   // diagonal (first maximal in-edge)
-                            if (bup + g > h) { h = bup + g; bdir = udir; }   // vertical only if strictly better
-                            const int left = (int)k1s_lds32(a_hist + so1) + g;
+                            if (bup + gq > h) { h = bup + gq; bdir = udir; }   // vertical only if strictly better
+                            const int left = (int)k1s_lds32(a_hist + so1) + gq;
                             if (left > h) { h = left; bdir = K5W_LEFT; }
                             if (!mode && h <= 0) { h = 0; bdir = K5W_STOP; }
                         } else {
                             // column 0: only vertical moves (global) or the free start (local)
-                            if (mode) { h = bup + g; bdir = udir; } else { h = 0; bdir = K5W_STOP; }
+                            if (mode) { h = bup + gq; bdir = udir; } else { h = 0; bdir = K5W_STOP; }
                         }
                         k1s_sts32(a_hist + so, (uint32_t)h);
-                        if (m.x & 0x20000u) H[goff] = h;
-                        DIR[goff] = (uint8_t)bdir;
+                        if (m.x & 0x20000u) *hout = h;
+                        *dirp = (uint8_t)bdir;
                         if (mode) {
                             if (j == L && (m.x & 0x40000u) && h > sinkv) { sinkv = h; sinki = r + 1; }
                         } else if (h >= bestv) {                 // rare: only cells on or next to the best path
