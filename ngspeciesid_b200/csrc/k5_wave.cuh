@@ -122,17 +122,18 @@ __global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
 #pragma unroll
                 for (int u = 0; u < K5W_FAST; ++u) pw[u] = none;
                 int np = 0;
+                bool has_far = false;
                 for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e], ++np) {
                     const int prow = G.rank[G.e_from[e]];       // 0-based row of the predecessor
                     const bool near = prow < r && (tr - prow / RPT) <= D - 2;
 #pragma unroll
                     for (int u = 0; u < K5W_FAST; ++u) if (u == np) pw[u] = near ? (uint32_t)prow : 0xffffu;
-                    if (np < K5W_FAST && !near) prank[(size_t)r * K5W_FAST + np] = prow + 1;
+                    if (np < K5W_FAST && !near) { prank[(size_t)r * K5W_FAST + np] = prow + 1; has_far = true; }
                 }
                 if (np == 0) { np = 1; pw[0] = (uint32_t)(V + tr); }        // source node: the virtual row 0
                 if (np > K5W_MAXE) { G.err = 7; }
                 const uint32_t info = (uint32_t)G.letter[v] | ((uint32_t)min(np, 255) << 8) | (np > K5W_FAST ? 0x10000u : 0u) |
-                                      (G.out_head[v] < 0 ? 0x40000u : 0u);
+                                      (G.out_head[v] < 0 ? 0x40000u : 0u) | (has_far ? 0x80000u : 0u);
                 smeta[2 * r] = make_uint4(info, pw[0] | (pw[1] << 16), pw[2] | (pw[3] << 16), pw[4] | (pw[5] << 16));
                 smeta[2 * r + 1] = make_uint4(pw[6] | (pw[7] << 16), pw[8] | (pw[9] << 16), pw[10] | (pw[11] << 16), 0u);
             }
@@ -208,7 +209,37 @@ __global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
                             if (pa > best) { best = pa; bdir = K5W_DIAG + (u); }                    \
                             if (pb > bup) { bup = pb; udir = K5W_UP + (u); }                        \
                         }
-                        if (!(m.x & 0x10000u)) {
+                        // all in-edges in the ring (the common case): no per-edge test for far rows
+#define K5W_PREDN(idx, u)                                                                           \
+                        {                                                                           \
+                            const uint32_t hp = s_hist + (idx) * row_b;                             \
+                            const int pa = (int)k1s_lds32(hp + so1), pb = (int)k1s_lds32(hp + so);  \
+                            if (pa > best) { best = pa; bdir = K5W_DIAG + (u); }                    \
+                            if (pb > bup) { bup = pb; udir = K5W_UP + (u); }                        \
+                        }
+                        if (!(m.x & 0x90000u)) {
+                            K5W_PREDN(m.y & 0xffffu, 0)
+                            K5W_PREDN(m.y >> 16, 1)                          // unused slots point at the -infinity row
+                            if (np > 2) {
+                                K5W_PREDN(m.z & 0xffffu, 2)
+                                K5W_PREDN(m.z >> 16, 3)
+                                if (np > 4) {
+                                    K5W_PREDN(m.w & 0xffffu, 4)
+                                    K5W_PREDN(m.w >> 16, 5)
+                                    if (np > 6) {
+                                        const uint4 m2 = k5w_lds128(a_meta + 16u);
+                                        K5W_PREDN(m2.x & 0xffffu, 6)
+                                        K5W_PREDN(m2.x >> 16, 7)
+                                        if (np > 8) {
+                                            K5W_PREDN(m2.y & 0xffffu, 8)
+                                            K5W_PREDN(m2.y >> 16, 9)
+                                            K5W_PREDN(m2.z & 0xffffu, 10)
+                                            K5W_PREDN(m2.z >> 16, 11)
+                                        }
+                                    }
+                                }
+                            }
+                        } else if (!(m.x & 0x10000u)) {
                             K5W_PRED(m.y & 0xffffu, 0)
                             K5W_PRED(m.y >> 16, 1)                           // unused slots point at the -infinity row
                             if (np > 2) {
@@ -242,6 +273,7 @@ __global__ void __launch_bounds__(K5W_THREADS, 1) k5w_poa_kernel(K5WArgs W)
                             }
                         }
 #undef K5W_PRED
+#undef K5W_PREDN
                         int h;
                         if (j >= 1) {
                             h = best + sc;                                   // diagonal (first maximal in-edge)
