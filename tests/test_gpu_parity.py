@@ -378,6 +378,16 @@ def test_k1_properties_at_scale(eng):
         exp = oc.minimizers(sc, k, w)
         got = [(decode_kmer(kmer[j], k), int(pos[j])) for j in range(starts[i], starts[i + 1])]
         assert got == exp
+    # the stream kernel hands out the record ranges per warp from an atomic cursor: sub-range
+    # fetches (inside a warp, across warps, single reads) and a second run of the kernel (new
+    # ranges) must return the same records as the full fetch
+    for b, e in [(0, 1), (5, 37), (31, 33), (1000, 1100), (49999, 50000), (12345, 23456)]:
+        lc2, c2, k2, p2 = eng.get_minimizers(b, e)
+        assert (lc2 == len_c[b:e]).all() and (c2 == counts[b:e]).all()
+        assert (k2 == kmer[starts[b]:starts[e]]).all() and (p2 == pos[starts[b]:starts[e]]).all()
+    eng.minimizers_timed(k, w, 2)
+    lc3, c3, k3, p3 = eng.get_minimizers()
+    assert (lc3 == len_c).all() and (c3 == counts).all() and (k3 == kmer).all() and (p3 == pos).all()
 
 
 # ---------------------------------------------------------------- sort stage (SURVEY.md 8 f, rank 1)
