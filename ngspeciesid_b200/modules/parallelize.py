@@ -76,6 +76,62 @@ def parallel_clustering(read_array, p_emp_probs, args):
             db.append(all_db[low])
 
 
+def parallel_clustering_ranks(read_array, p_emp_probs, args, group=None, cluster_fn=None):
+    """`parallel_clustering` with the batches of every round sharded over the ranks of a
+    torch.distributed process group (one process per GPU; NCCL on the GPU box, gloo in the CPU
+    tests). Every rank passes the same score-sorted `read_array`; batch i of a round runs on rank
+    i mod world_size, so the result depends on --t (args.nr_cores) exactly as in the reference and
+    NOT on the number of GPUs, and every rank returns the same (clusters, representatives).
+
+    The only exchange is the one the reference has when it joins its process pool
+    (modules/parallelize.py:153-187): the (clusters, representatives, minimizer_database, batch
+    index) tuples of the finished batches, here one all_gather_object per round. After round 1
+    these hold the surviving representatives only (tens to thousands of reads).
+
+    `cluster_fn` replaces cluster.reads_to_clusters; the CPU tests pass the oracle's restatement
+    (the product path needs a GPU)."""
+    import torch.distributed as dist
+    fn = cluster_fn if cluster_fn is not None else cluster.reads_to_clusters
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    batches = list(batch_list(read_array, args.nr_cores, batch_type=args.batch_type))
+    num = args.nr_cores
+    cl = [{r[0]: [r[2]] for r in b} for b in batches]
+    rp = [{r[0]: tuple(r) for r in b} for b in batches]
+    db = [{} for _ in batches]
+    while True:
+        if len(batches) == 1:
+            # last round runs in one process in the reference too (parallelize.py:142-149)
+            out = [None, None]
+            if rank == 0:
+                res = fn(cl[0], rp[0], batches[0], p_emp_probs, db[0], 1, args)
+                out = [res[1][0], res[1][1]]
+            dist.broadcast_object_list(out, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            return out[0], out[1]
+        mine = []
+        for i in range(rank, len(batches), world):
+            res = fn(cl[i], rp[i], batches[i], p_emp_probs, db[i], i + 1, args)
+            mine.append(res[i + 1])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        all_cl, all_rp, all_db = {}, {}, {}
+        for c, r, d, bi in sorted((t for g in gathered for t in g), key=lambda t: t[3]):
+            all_cl.update(c)
+            all_rp.update(r)
+            all_db[bi] = d
+        read_array = [(v[0], v[1], v[2], v[3], v[4], v[5]) for _, v in
+                      sorted(all_rp.items(), key=lambda x: x[1][5], reverse=True)]
+        if num == 1:
+            return all_cl, all_rp
+        batches = list(batch_list(read_array, num, batch_type=args.batch_type, merge_consecutive=True))
+        num = len(batches)
+        cl, rp, db = [], [], []
+        for b in batches:
+            low = min(r[1] for r in b)
+            cl.append({r[0]: all_cl[r[0]] for r in b})
+            rp.append({r[0]: all_rp[r[0]] for r in b})
+            db.append(all_db[low])
+
+
 def single_clustering(read_array, p_emp_probs, args):
     """Reference: NGSpeciesID:20-33."""
     clusters = {r[0]: [r[2]] for r in read_array}

@@ -2,6 +2,7 @@
 vectors. Everything here needs a B200 (`-m gpu`)."""
 import ctypes
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -275,6 +276,29 @@ def _run_scenario(tag, p_table):
                                  "synth2k_t1", "synth2k_t8", "synthpb_t1"])
 def test_clustering_matches_reference_golden(tag, p_table):
     _run_scenario(tag, p_table)
+
+
+@pytest.mark.gpu
+def test_rank_sharded_driver_on_gpu(p_table):
+    """parallelize.parallel_clustering_ranks with the GPU operator (single-rank process group here;
+    the world_size-2/3 exchange is covered on the CPU by tests/test_ranks_gloo.py)."""
+    import torch.distributed as dist
+    from ngspeciesid_b200.modules import parallelize
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29917")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        g = load_golden("clusters_h1_t4.json.gz")
+        args = scenario_args(g)
+        args.device = 0
+        ra = oc.read_array_from_sorted(oc.sort_stage(scenario_reads("h1_t4"), args.k))
+        p_emp = oc.load_p_emp(p_table, args.k, args.w)
+        clusters, reps = parallelize.parallel_clustering_ranks(ra, p_emp, args)
+        idx_of = {r[2]: r[0] for r in ra}
+        got = [[idx_of[a] for a in accs] for _rep, accs in oc.output_order(clusters, reps)]
+        assert got == g["clusters"]
+    finally:
+        dist.destroy_process_group()
 
 
 def _mixed_reads(n, seed):
