@@ -137,7 +137,25 @@ struct MapArgs {
     AlignRequest *req;
     int32_t *req_n;
     int32_t *err_flag;
+    // Alignment prefetch for the tentative representatives of a tile (see ngsid_cluster): results
+    // of pairs (tentative read, slot) aligned ahead of the order-dependent resolution.
+    // spec_mat[row * spec_cols + slot] = -1 unknown / 0 failed / 1 passed, row = spec_u[pos - spec_lo].
+    const int32_t *spec_u;          // nullptr: no prefetch table
+    int8_t *spec_mat;
+    int spec_lo, spec_hi, spec_cols;
+    int spec_mode;                  // 1: this launch only emits the prefetch requests
 };
+
+// gap open penalty and match_id of a (read, representative) pair (cluster.py:185-198)
+__device__ __forceinline__ AlignRequest make_align_request(const MapArgs &A, int pos, int slot, int read, int k)
+{
+    const int rep_read = A.slot_read[slot];
+    double es = __dadd_rn(A.erru[read], A.erru[rep_read]);
+    int go = (es <= 0.01) ? 5 : (es <= 0.04) ? 4 : (es <= 0.1) ? 3 : 2;
+    int mid = (int)floor(__dmul_rn(__dadd_rn(1.0, -es), (double)k));
+    AlignRequest rq = {pos, slot, read, rep_read, go, mid};
+    return rq;
+}
 
 // rank key of cluster.py:79 / :174, descending: (n_hits, sum of positions, accession string)
 __device__ __forceinline__ bool key_greater(uint32_t n1, uint32_t s1, uint32_t a1,
@@ -183,7 +201,8 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
             while (node >= 0) {
                 PostingNode pn = A.table.nodes[node];
                 int s = pn.slot;
-                if (A.slot_state[s] == SLOT_VALID && A.slot_pos[s] < pos) {
+                const uint8_t stt = A.slot_state[s];
+                if ((stt == SLOT_VALID || (A.spec_mode && stt == SLOT_TENTATIVE)) && A.slot_pos[s] < pos) {
                     uint32_t old = atomicAdd(&cnt[s], 1u);
                     atomicAdd(&spos[s], mj.y);
                     if (old == 0) touched[atomicAdd(ntouched, 1u)] = (uint32_t)s;
@@ -194,6 +213,35 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
         __threadfence_block();
         __syncwarp();
         const int nt = (int)*ntouched;
+
+        if (A.spec_mode) {
+            // Prefetch pass: whatever subset of the tentative slots survives, an alignment of this
+            // read is only ever asked for a slot whose hit count equals the top count of that
+            // world, which is >= min_shared and >= the best count among the certain slots. Ask for
+            // every (read, slot) pair above that bound that is not known yet.
+            uint32_t topc = 0;
+            for (int t = lane; t < nt; t += 32) {
+                const int s = (int)touched[t];
+                if (A.slot_state[s] == SLOT_VALID) topc = max(topc, cnt[s]);
+            }
+            for (int d = 16; d > 0; d >>= 1) topc = max(topc, __shfl_xor_sync(NGSID_FULL_MASK, topc, d));
+            const uint32_t thr = max(topc, (uint32_t)max(P.min_shared, 1));
+            const int row = A.spec_u[pos - A.spec_lo];
+            const AlignCacheEntry *ac = A.acache + (size_t)pos * ACACHE_N;
+            for (int t = lane; t < nt; t += 32) {
+                const int s = (int)touched[t];
+                bool ask = row >= 0 && s < A.spec_cols && cnt[s] >= thr;
+                for (int e = 0; e < ACACHE_N; ++e) if (ac[e].slot == s) ask = false;
+                if (ask && A.spec_mat[(size_t)row * A.spec_cols + s] < 0)
+                    A.req[atomicAdd(A.req_n, 1)] = make_align_request(A, pos, s, read, P.k);
+            }
+            for (int t = lane; t < nt; t += 32) {
+                const int s = (int)touched[t];
+                cnt[s] = 0; spos[s] = 0;
+            }
+            __syncwarp();
+            continue;
+        }
 
         int decision = DEC_NEW;
         int via = 0;
@@ -303,18 +351,14 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
                     int cached = -1;                      // -1 unknown, 0 failed, 1 passed
                     for (int e = 0; e < ACACHE_N; ++e)
                         if (ac[e].slot == bslot) cached = ac[e].passed;
+                    if (cached < 0 && A.spec_u && pos >= A.spec_lo && pos < A.spec_hi && bslot < A.spec_cols) {
+                        const int row = A.spec_u[pos - A.spec_lo];
+                        if (row >= 0) cached = (int)A.spec_mat[(size_t)row * A.spec_cols + bslot];
+                    }
                     if (cached == 1) { decision = A.slot_read[bslot]; via = 2; break; }
                     if (cached == 0) continue;
                     // not aligned yet: ask for it (one candidate per round, like the reference)
-                    if (lane == 0) {
-                        const int rep_read = A.slot_read[bslot];
-                        double es = __dadd_rn(A.erru[read], A.erru[rep_read]);
-                        int go = (es <= 0.01) ? 5 : (es <= 0.04) ? 4 : (es <= 0.1) ? 3 : 2;
-                        int mid = (int)floor(__dmul_rn(__dadd_rn(1.0, -es), (double)P.k));
-                        int ri = atomicAdd(A.req_n, 1);
-                        AlignRequest rq = {pos, bslot, read, rep_read, go, mid};
-                        A.req[ri] = rq;
-                    }
+                    if (lane == 0) A.req[atomicAdd(A.req_n, 1)] = make_align_request(A, pos, bslot, read, P.k);
                     decision = DEC_NEED_ALIGN;
                     break;
                 }
@@ -355,6 +399,24 @@ __global__ void k2_apply_align_kernel(const AlignRequest *__restrict__ req, int 
     ac[e].slot = rq.slot;
     ac[e].passed = passed;
     list_out[i] = rq.pos;
+}
+
+// the same for the prefetched pairs: one cell of the prefetch table per request
+__global__ void k2_apply_spec_kernel(const AlignRequest *__restrict__ req, int n_req,
+                                     const int32_t *__restrict__ k4cnt, const int64_t *__restrict__ off,
+                                     const DeviceClusterParams *__restrict__ params,
+                                     const int32_t *__restrict__ spec_u, int spec_lo, int spec_cols,
+                                     int8_t *__restrict__ spec_mat, int32_t *err_flag)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_req) return;
+    AlignRequest rq = req[i];
+    double n1 = (double)(off[rq.read_a + 1] - off[rq.read_a]);
+    double n2 = (double)(off[rq.read_b + 1] - off[rq.read_b]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(err_flag + 2), (unsigned long long)(n1 * n2));
+    double ratio = __ddiv_rn((double)k4cnt[i], n1);
+    if (params->symmetric) ratio = fmin(ratio, __ddiv_rn((double)k4cnt[i], n2));
+    spec_mat[(size_t)spec_u[rq.pos - spec_lo] * spec_cols + rq.slot] = ratio >= params->aligned_threshold ? 1 : 0;
 }
 
 __global__ void k2_fill_acache_kernel(AlignCacheEntry *ac, int64_t n)

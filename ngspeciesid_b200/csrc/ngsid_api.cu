@@ -777,8 +777,8 @@ struct ClusterRun {
     DevBuf keys_alt, heads_alt;        // spare pair for growth
     int64_t pairs_inserted = 0;
     int scap = 0, map_warps = 0, map_blocks = 0;
-    DevBuf d_list2, d_err;
-    std::vector<int32_t> h_dec;
+    DevBuf d_list2, d_err, d_spec_u, d_spec_mat;
+    std::vector<int32_t> h_dec, h_spec_u;
     ngsid_cluster_stats st;
     MapArgs A;
 
@@ -789,6 +789,7 @@ struct ClusterRun {
     int insert_slots(int slot0, int count);
     int run_map(const int32_t *d_list, int n_list);
     int fetch_dec(int lo, int hi);
+    int prefetch_alignments(const std::vector<int32_t> &U, int lo, int hi);
 };
 
 int ClusterRun::ensure_table(int64_t pairs_after)
@@ -824,7 +825,9 @@ int ClusterRun::ensure_scratch(int slots_after)
     // warps in flight bounded by a 6 GB scratch budget
     int64_t budget = (int64_t)6 << 30;
     int64_t max_warps = budget / ((int64_t)ncap * 12);
-    int blocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, std::max<int64_t>(1, max_warps / 8));
+    int bps = 4;                                                     // blocks of 8 warps per SM (48 registers: up to 5)
+    if (const char *e = getenv("NGSID_MAP_BPS")) bps = std::max(1, std::min(8, atoi(e)));
+    int blocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * bps, std::max<int64_t>(1, max_warps / 8));
     map_blocks = blocks;
     map_warps = blocks * 8;
     size_t bytes = (size_t)map_warps * 12 * ncap;
@@ -910,6 +913,50 @@ int ClusterRun::run_map(const int32_t *d_list, int n_list)
         list = d_list2.as<int32_t>();
         nl = nreq;
     }
+}
+
+// Alignment prefetch for the tentative representatives U[1..] of the tile [lo, hi). Their
+// resolution is a chain (one batch per new representative) and every batch would otherwise pay
+// the latency of its own small K4 launches. The alignment statistic depends on the pair only, so
+// one launch aligns every (tentative read, earlier slot) pair that some batch could ask for
+// (k2_map_kernel, spec_mode) and the batches find the results in the prefetch table.
+int ClusterRun::prefetch_alignments(const std::vector<int32_t> &U, int lo, int hi)
+{
+    const int rows = (int)U.size() - 1, cols = n_slots;
+    h_spec_u.assign((size_t)(hi - lo), -1);
+    for (int u = 1; u <= rows; ++u) h_spec_u[U[u] - lo] = u - 1;
+    CUDA_TRY(ctx, d_spec_u.ensure((size_t)(hi - lo) * 4 + 64));
+    CUDA_TRY(ctx, d_spec_mat.ensure((size_t)rows * cols + 64));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_spec_u.p, h_spec_u.data(), (size_t)(hi - lo) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(d_spec_mat.p, 0xff, (size_t)rows * cols, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_list.p, U.data() + 1, (size_t)rows * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_reqn.p, 0, 4, ctx->stream));
+    A.spec_u = d_spec_u.as<int32_t>();
+    A.spec_mat = d_spec_mat.as<int8_t>();
+    A.spec_lo = lo; A.spec_hi = hi; A.spec_cols = cols;
+    A.list = ctx->d_list.as<int32_t>(); A.n_list = rows;
+    A.spec_mode = 1;
+    ev_begin(ctx, 5);
+    k2_map_kernel<<<std::min(map_blocks, (rows + 7) / 8), 256, 0, ctx->stream>>>(A);
+    ev_end(ctx);
+    A.spec_mode = 0;
+    KERNEL_CHECK(ctx);
+    int32_t nreq = 0;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&nreq, ctx->d_reqn.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nreq == 0) return NGSID_OK;
+    const AlignRequest *rq = ctx->d_req.as<AlignRequest>();
+    ev_begin(ctx, 4);
+    int rc = k4_dispatch(ctx, &rq->read_a, &rq->read_b, &rq->open, &rq->match_id, 6, nreq, ctx->k,
+                         ctx->d_k4cnt.as<int32_t>(), nullptr);
+    ev_end(ctx);
+    if (rc) return rc;
+    st.n_alignments += nreq;
+    k2_apply_spec_kernel<<<(nreq + 255) / 256, 256, 0, ctx->stream>>>(rq, nreq, ctx->d_k4cnt.as<int32_t>(),
+                                                                      ctx->d_off.as<int64_t>(), A.params, A.spec_u,
+                                                                      A.spec_lo, A.spec_cols, A.spec_mat, d_err.as<int32_t>());
+    KERNEL_CHECK(ctx);
+    return NGSID_OK;
 }
 
 int ClusterRun::fetch_dec(int lo, int hi)
@@ -1015,7 +1062,12 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     R.slot_read.reserve(max_slots); R.slot_pos.reserve(max_slots); R.slot_state.reserve(max_slots);
     R.h_dec.assign(n, DEC_NEW);
 
-    auto cleanup = [&](int code) { R.keys_alt.release(); R.heads_alt.release(); R.d_list2.release(); R.d_err.release(); return code; };
+    auto cleanup = [&](int code) {
+        R.keys_alt.release(); R.heads_alt.release(); R.d_list2.release(); R.d_err.release();
+        R.d_spec_u.release(); R.d_spec_mat.release();
+        return code;
+    };
+    const bool use_prefetch = getenv("NGSID_NO_PREFETCH") == nullptr;
 
     // ---- initial representatives (merge rounds of modules/parallelize.py:196-215)
     for (int64_t i = 0; i < n_init; ++i) {
@@ -1036,6 +1088,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     while (pos < n) {
         const int hi = std::min(n, pos + T);
         R.st.n_tiles++;
+        A.spec_u = nullptr;
         // ---- phase 1: speculative pass against the representatives known before the tile
         k2_iota_kernel<<<(hi - pos + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_list.as<int32_t>(), pos, hi - pos);
         KERNEL_CHECK(ctx);
@@ -1056,6 +1109,12 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
         R.n_slots += (int)U.size();
         rc = R.insert_slots(slot0, (int)U.size());
         if (rc) return cleanup(rc);
+
+        // ---- alignment prefetch for the chain below (request buffer: n entries)
+        if (use_prefetch && U.size() >= 3 && (int64_t)(U.size() - 1) * R.n_slots <= (int64_t)n) {
+            rc = R.prefetch_alignments(U, pos, hi);
+            if (rc) return cleanup(rc);
+        }
 
         // ---- phase 2: resolve the tentative ones in order against the certain ones before them.
         // All unresolved ones are mapped in one batch against the representatives that are certain
