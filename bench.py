@@ -430,6 +430,27 @@ def run_ours(args):
                                                     "sample": "first %d reads, oracle/cluster_oracle.py" % ns_}
             result["sort_stage"]["parity_sample_identical"] = bool(ref_sc == [float(x) for x in sc[:ns_]])
 
+    # ---- ingest in front of the sort stage (SURVEY.md 8 f rank 3): host C parser vs the generator
+    if rank == 0 and not args.no_consensus:
+        import io
+        from ngspeciesid_b200.modules import help_functions as hf
+        ni = min(n_mine, 20000)
+        text = "".join("@%s\n%s\n+\n%s\n" % (my_acc[i], s_seq[s_off[i]:s_off[i + 1]].tobytes().decode(),
+                                               s_qual[s_off[i]:s_off[i + 1]].tobytes().decode()) for i in range(ni))
+        data = text.encode()
+        t5 = time.perf_counter()
+        fa = hf.parse_fastq_bytes(data)
+        dt5 = time.perf_counter() - t5
+        t6 = time.perf_counter()
+        n_py = sum(1 for _ in hf.readfq(io.StringIO(text)))
+        dt6 = time.perf_counter() - t6
+        result["ingest"] = {"metric": "FASTQ bytes/s parsed into upload-ready arrays (ngsid_fastq_parse, host, 1 thread)",
+                            "value": len(data) / dt5, "unit": "B/s", "reads": int(len(fa)), "bytes": len(data),
+                            "cpu_baseline": {"value": len(data) / dt6, "unit": "B/s", "cores": 1, "kind": "port",
+                                             "sample": "the same %d records through the readfq generator mirror" % n_py},
+                            "parity_identical": bool(len(fa) == n_py == ni and (fa.seq == s_seq[:s_off[ni]]).all()
+                                                     and (fa.qual == s_qual[:s_off[ni]]).all())}
+
     # ---- K1 roofline on a replicated input far larger than L2 (rank 0 only)
     if rank == 0 and not args.no_roofline:
         rep = max(1, int(args.roofline_reads // max(1, n_mine)))

@@ -167,6 +167,21 @@ int ngsid_sg_align_paths(ngsid_ctx *ctx, const int32_t *a, const int32_t *b, con
 int ngsid_sort_scores(ngsid_ctx *ctx, int k, const double *phred_p_capped, const double *phred_p_uncapped,
                       double *out_score, double *out_err_rate);
 
+/* ---- FASTA/FASTQ ingest (host code, no context, no GPU) --------------------------------------
+ * Replaces: modules/help_functions.py:13-42 (readfq, lh3's generator) for a whole file held in
+ * memory, with the line model of Python's text mode 'r' that the reference opens its input with
+ * (get_sorted_fastq_for_cluster.py:126, NGSpeciesID:54): "\n", "\r\n" and "\r" end a line.
+ * Record i: name = buf[name_off[i], +name_len[i]) (the whole header line after '@' / '>'),
+ * sequence = seq_out[seq_off[i], seq_off[i+1]), quality = qual_out[qual_off[i], qual_off[i+1])
+ * if has_qual[i] (0 = FASTA record / quality cut short by the end of the file: the reference
+ * yields None). seq_out / qual_out need `len` bytes, the per-record arrays cap_records (+1 for the
+ * offsets). With seq_out == NULL only *n_records is computed. Returns NGSID_EINVAL (and the needed
+ * count in *n_records) when cap_records is too small. The reference's quirks are kept: the last
+ * line of a file without a final newline loses its last character.                              */
+int ngsid_fastq_parse(const uint8_t *buf, int64_t len, int64_t cap_records,
+                      uint8_t *seq_out, uint8_t *qual_out, int64_t *name_off, int32_t *name_len,
+                      int64_t *seq_off, int64_t *qual_off, uint8_t *has_qual, int64_t *n_records);
+
 /* ---- K5: partial-order-alignment consensus ---------------------------------------------------
  * Replaces: the spoa call of consensus.run_spoa (modules/consensus.py:83-92: local alignment,
  * match 5, mismatch -4, linear gap -2, quality weights, heaviest-bundle consensus) and the

@@ -11,7 +11,8 @@ LIB_PATH = os.path.join(_HERE, "libngsid.so")
 EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last_error",
            "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
-           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus"]
+           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus",
+           "ngsid_fastq_parse"]
 
 
 class ClusterParams(ctypes.Structure):
@@ -77,6 +78,7 @@ def load():
     lib.ngsid_sg_block_align.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.ngsid_sg_align_paths.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp]
     lib.ngsid_poa_consensus.argtypes = [vp, P(PoaParams), i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
+    lib.ngsid_fastq_parse.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, P(i64)]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

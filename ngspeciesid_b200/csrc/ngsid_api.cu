@@ -7,6 +7,7 @@
 #include "k1_minimizers.cuh"
 #include "k0_sortscore.cuh"
 #include "k1_stream.cuh"
+#include "fastq_ingest.cuh"
 #include "k2_map.cuh"
 #include "k4_align.cuh"
 #include "k4_trace.cuh"
@@ -163,6 +164,19 @@ extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint
         return fail(ctx, NGSID_EUNSUPPORTED, "a read contains a base outside ACGT (unsupported in this build)");
     }
     return NGSID_OK;
+}
+
+// ================================================================================ ingest (host)
+extern "C" int ngsid_fastq_parse(const uint8_t *buf, int64_t len, int64_t cap_records,
+                                 uint8_t *seq_out, uint8_t *qual_out, int64_t *name_off, int32_t *name_len,
+                                 int64_t *seq_off, int64_t *qual_off, uint8_t *has_qual, int64_t *n_records)
+{
+    if (len < 0 || (len > 0 && !buf) || cap_records < 0 || !n_records) return NGSID_EINVAL;
+    const bool wr = seq_out != nullptr;
+    if (wr && (!qual_out || !name_off || !name_len || !seq_off || !qual_off || !has_qual)) return NGSID_EINVAL;
+    fastq_ingest::Out O = {cap_records, 0, seq_out, qual_out, name_off, name_len, seq_off, qual_off, has_qual, 0, 0};
+    *n_records = fastq_ingest::parse(buf, len, O);
+    return (wr && *n_records > cap_records) ? NGSID_EINVAL : NGSID_OK;
 }
 
 // ================================================================================ K1

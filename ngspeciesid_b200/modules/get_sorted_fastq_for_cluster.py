@@ -45,16 +45,9 @@ def _threshold_error_rate(q_threshold):
             return e
 
 
-def score_records(records, k, q_threshold, eng=None):
-    """records: [(acc, seq, qual)] in file order -> (read_array, error_rates) exactly as
-    fastq_single_core / fastq_parallel build them (reference :124-155, :41-66): read_array =
-    [(acc, seq, qual, score)] sorted by score descending (stable), error_rates of the kept reads
-    in file order."""
-    eng = eng or _engine.get_engine()
-    records = list(records)
-    if not records:
-        return [], []
-    eng.upload_records([(s, q) for _a, s, q in records])
+def _score_uploaded(eng, k, q_threshold):
+    """Scores, filter and stable order of the reads currently uploaded to `eng` -> (order, kept
+    indices in file order, score, err): reference :124-155 / :41-66 with the arithmetic on the GPU."""
     score, err = eng.sort_scores(k)
     seqb = eng.h_seq
     off = eng.offsets
@@ -71,15 +64,48 @@ def score_records(records, k, q_threshold, eng=None):
     e_star = _threshold_error_rate(q_threshold)
     keep &= ~(err >= e_star)
     idx = np.nonzero(keep)[0]
-    error_rates = [float(err[i]) for i in idx]
     order = idx[np.argsort(-score[idx], kind="stable")]
+    return order, idx, score, err
+
+
+def score_records(records, k, q_threshold, eng=None):
+    """records: [(acc, seq, qual)] in file order -> (read_array, error_rates) exactly as
+    fastq_single_core / fastq_parallel build them (reference :124-155, :41-66): read_array =
+    [(acc, seq, qual, score)] sorted by score descending (stable), error_rates of the kept reads
+    in file order."""
+    eng = eng or _engine.get_engine()
+    records = list(records)
+    if not records:
+        return [], []
+    eng.upload_records([(s, q) for _a, s, q in records])
+    order, idx, score, err = _score_uploaded(eng, k, q_threshold)
+    error_rates = [float(err[i]) for i in idx]
     read_array = [(records[i][0], records[i][1], records[i][2], float(score[i])) for i in order]
     return read_array, error_rates
 
 
+def score_fastq_arrays(fa, k, q_threshold, eng=None):
+    """The same for a file parsed by help_functions.read_fastq_arrays (ngsid_fastq_parse): the
+    concatenated arrays go to the GPU as they are and Python strings are only made for the reads
+    that pass the filter."""
+    eng = eng or _engine.get_engine()
+    if len(fa) == 0:
+        return [], []
+    if not fa.has_qual.all() or (np.diff(fa.seq_off) != np.diff(fa.qual_off)).any():
+        # FASTA records or qualities longer than the read: the generic record path decides
+        return score_records([(n, s, q) for n, (s, q) in fa.records()], k, q_threshold, eng)
+    eng.upload(fa.seq, fa.qual, fa.seq_off)
+    order, idx, score, err = _score_uploaded(eng, k, q_threshold)
+    error_rates = [float(err[i]) for i in idx]
+    read_array = []
+    for i in order:
+        name, (s, q) = fa.record(i)
+        read_array.append((name, s, q, float(score[i])))
+    return read_array, error_rates
+
+
 def fastq_single_core(args):
-    recs = [(acc, seq, qual) for acc, (seq, qual) in help_functions.readfq(open(args.fastq, 'r'))]
-    return score_records(recs, args.k, args.quality_threshold)
+    return score_fastq_arrays(help_functions.read_fastq_arrays(args.fastq), args.k, args.quality_threshold)
 
 
 def fastq_parallel(args):
