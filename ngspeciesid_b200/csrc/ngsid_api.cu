@@ -493,9 +493,11 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
                  have_aux ? ctx->d_auxseq.as<uint8_t>() : nullptr, have_aux ? ctx->d_aoff.as<int64_t>() : nullptr};
     for (int64_t p0 = 0; p0 < n_pairs; p0 += slots) {
         const int64_t c = std::min<int64_t>(slots, n_pairs - p0);
-        // fewer pairs than the one-warp-per-pair shape needs to fill half the machine: take the latency shape
+        // fewer pairs than the one-warp-per-pair shape has resident warps: take the latency shape (a lone
+        // warp needs 0.83 ms for a 750 x 750 pair, a block of strips 0.29 ms; A/B on the bench: +5 %)
+        static const double multi_factor = getenv("NGSID_K4_MULTI_FACTOR") ? atof(getenv("NGSID_K4_MULTI_FACTOR")) : 1.0;
         const bool multi = multi_ok && ctx->k4_shape != 1 &&
-                           (ctx->k4_shape == 2 || c * 2 <= (int64_t)ctx->sm_count * bps * wpb / W);
+                           (ctx->k4_shape == 2 || (double)c * multi_factor <= (double)((int64_t)ctx->sm_count * bps * wpb / W));
         if (multi) {
             int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c, (int64_t)ctx->sm_count * bps_multi));
             k4t_dp_kernel<true><<<blocks, W * 32, smem_multi, ctx->stream>>>(Q, pa, pb, po, stride, p0, c, n2cap,
@@ -839,7 +841,7 @@ int ClusterRun::ensure_scratch(int slots_after)
     // warps in flight bounded by a 6 GB scratch budget
     int64_t budget = (int64_t)6 << 30;
     int64_t max_warps = budget / ((int64_t)ncap * 12);
-    int bps = 4;                                                     // blocks of 8 warps per SM (48 registers: up to 5)
+    int bps = 5;                                                     // blocks of 8 warps per SM (48 registers: 5 fit)
     if (const char *e = getenv("NGSID_MAP_BPS")) bps = std::max(1, std::min(8, atoi(e)));
     int blocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * bps, std::max<int64_t>(1, max_warps / 8));
     map_blocks = blocks;
@@ -1095,8 +1097,13 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     rc = R.insert_slots(0, R.n_slots);
     if (rc) return cleanup(rc);
 
+    // tiles grow 32 -> x8 -> ... -> 65536: every tile costs the latency of its own map / K4 / traceback
+    // rounds (>= 0.6 ms), new representatives come early in a score-sorted amplicon set (A/B on the
+    // bench: growth 2 / 4 / 8 / 16 = 2.41 / 2.60 / 2.68 / 2.52 M reads/s)
     const int tmax = params->tile_reads > 0 ? params->tile_reads : 65536;
-    int T = std::min(32, tmax);
+    const int tgrow = getenv("NGSID_TILE_GROWTH") ? std::max(2, atoi(getenv("NGSID_TILE_GROWTH"))) : 8;
+    const int tfirst = getenv("NGSID_TILE_FIRST") ? std::max(1, atoi(getenv("NGSID_TILE_FIRST"))) : 32;
+    int T = std::min(tfirst, tmax);
     int pos = 0;
     std::vector<int32_t> U, h_list;
     while (pos < n) {
@@ -1112,7 +1119,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
         if (rc) return cleanup(rc);
         U.clear();
         for (int i = pos; i < hi; ++i) if (R.h_dec[i] == DEC_NEW) U.push_back(i);
-        if (U.empty()) { pos = hi; T = std::min(T * 2, tmax); continue; }
+        if (U.empty()) { pos = hi; T = (int)std::min<int64_t>((int64_t)T * tgrow, tmax); continue; }
 
         // ---- tentative representatives; the first one is certain
         const int slot0 = R.n_slots;
@@ -1176,7 +1183,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
             if (rc) return cleanup(rc);
             for (int i : h_list) if (R.h_dec[i] == DEC_NEW) { surprise = i; break; }
         }
-        if (surprise < 0) { pos = hi; T = std::min(T * 2, tmax); continue; }
+        if (surprise < 0) { pos = hi; T = (int)std::min<int64_t>((int64_t)T * tgrow, tmax); continue; }
 
         // ---- a read that had been assigned became a representative: everything after it in the
         // tile is re-done with it in the table

@@ -1,9 +1,11 @@
-timeout 400 python -m pytest tests -m gpu -x -q -k "clustering or golden or many_representatives or rank_sharded" 2>&1 | tail -4
-for v in "A=1" "NGSID_NO_PREFETCH=1" "NGSID_MAP_BPS=4" "NGSID_MAP_BPS=3"; do
-  env $v timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu --no-consensus --no-roofline > gpurun_out/bench_p.json 2> gpurun_out/bench_p.err
-  python - "$v" <<'P'
+#!/bin/bash
+# A/B runs of the clustering step on one B200: each line = one environment setting
+run() {
+  env $1 timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu --no-consensus --no-roofline $BENCH_ARGS > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err
+  python - "$1" <<'P'
 import json,sys
-d=json.loads([l for l in open("gpurun_out/bench_p.json") if l.startswith("{")][-1])
-print(sys.argv[1], round(d["value"]), round(d["e2e"]["value"]), d["phase_ms_per_step"], {k:d["cluster_stats"][k] for k in ("n_alignments","n_chain_steps","n_tiles","n_new_reps","n_aln_passed","n_mapped")}, d["gpu_launches"])
+d=json.loads([l for l in open("gpurun_out/bench_ab.json") if l.startswith("{")][-1])
+print(sys.argv[1], round(d["value"]), round(d["e2e"]["value"]), {k: round(v,2) for k,v in d["phase_ms_per_step"].items()}, {k:d["cluster_stats"][k] for k in ("n_alignments","n_chain_steps","n_tiles","n_map_launch_reads")}, d["gpu_launches"])
 P
-done
+}
+for v in "$@"; do run "$v"; done
