@@ -180,6 +180,47 @@ def merge_rounds(eng, params, acc_rank, batch_results, n_batches):
     return merges, cur[min(cur)]
 
 
+def batch_bounds(lens, world):
+    """Read index bounds of the `world` consecutive batches of the score-sorted list
+    (modules/parallelize.py:54-67: cut after the read that fills int(total_nt / N) + 1 nucleotides)."""
+    n_total = len(lens)
+    bounds = [0]
+    if world > 1:
+        limit = int(lens.sum() / world) + 1
+        csum = np.cumsum(lens)
+        base = 0
+        while len(bounds) < world:
+            j = int(np.searchsorted(csum, base + limit, side="left"))
+            if j >= n_total:
+                break
+            bounds.append(j + 1)
+            base = int(csum[j])
+    while len(bounds) < world + 1:
+        bounds.append(n_total)
+    return bounds
+
+
+def merge_representatives(eng2, seq, qual, offsets, acc, gathered, params):
+    """gathered[b] = global read ids of the representatives batch b ended with. Uploads these reads
+    only, runs the merge rounds and returns ({merged representative: winner}, final representatives),
+    both in global read ids."""
+    from ngspeciesid_b200 import engine as E
+    ids = sorted(set(x for g in gathered for x in g))
+    if not ids:
+        return {}, []
+    idx = {g: i for i, g in enumerate(ids)}
+    parts = [slice_reads(seq, qual, offsets, g, g + 1) for g in ids]
+    m_seq = np.concatenate([p[0] for p in parts]); m_qual = np.concatenate([p[1] for p in parts])
+    m_off = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum([len(p[0]) for p in parts], out=m_off[1:])
+    eng2.upload(m_seq, m_qual, m_off)
+    eng2.minimizers(K, W)
+    eng2.quality_stats()
+    ar = E.accession_ranks([acc[g] for g in ids])
+    merges, final = merge_rounds(eng2, params, ar, {b + 1: [idx[x] for x in g] for b, g in enumerate(gathered)}, len(gathered))
+    return {ids[a]: ids[b] for a, b in merges.items()}, [ids[i] for i in final]
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -201,21 +242,7 @@ def run_ours(args):
     params = {"max_gap": E.max_gap_table(p_emp, 0.1)}
 
     # --t N semantics: N consecutive batches of the score-sorted list by cumulative nucleotides
-    lens = np.diff(offsets)
-    bounds = [0]
-    if world > 1:
-        # modules/parallelize.py:54-67: cut after the read that fills int(total_nt / N) + 1 nucleotides
-        limit = int(lens.sum() / world) + 1
-        csum = np.cumsum(lens)
-        base = 0
-        while len(bounds) < world:
-            j = int(np.searchsorted(csum, base + limit, side="left"))
-            if j >= n_total:
-                break
-            bounds.append(j + 1)
-            base = int(csum[j])
-    while len(bounds) < world + 1:
-        bounds.append(n_total)
+    bounds = batch_bounds(np.diff(offsets), world)
     lo, hi = bounds[rank], bounds[rank + 1]
     n_mine = hi - lo
 
@@ -253,23 +280,8 @@ def run_ours(args):
     def merge_on_rank0():
         """Merge rounds over the representatives of all batches (few hundred reads at most):
         run once on rank 0 inside the timed region of every step."""
-        gathered = state["gathered"]
-        ids = sorted(set(x for g in gathered for x in g))
-        if not ids:
-            return {}, []
-        # small separate upload of the representatives only
-        idx = {g: i for i, g in enumerate(ids)}
-        parts = [slice_reads(seq, qual, offsets, g, g + 1) for g in ids]
-        m_seq = np.concatenate([p[0] for p in parts]); m_qual = np.concatenate([p[1] for p in parts])
-        m_off = np.zeros(len(ids) + 1, dtype=np.int64)
-        np.cumsum([len(p[0]) for p in parts], out=m_off[1:])
         eng2 = state.setdefault("eng2", E.Engine(local))
-        eng2.upload(m_seq, m_qual, m_off)
-        eng2.minimizers(K, W)
-        eng2.quality_stats()
-        ar = E.accession_ranks([acc[g] for g in ids])
-        merges, final = merge_rounds(eng2, params, ar, {b + 1: [idx[x] for x in g] for b, g in enumerate(gathered)}, world)
-        return merges, final
+        return merge_representatives(eng2, seq, qual, offsets, acc, state["gathered"], params)
 
     def full_step(e2e):
         step(e2e)

@@ -301,6 +301,56 @@ def test_rank_sharded_driver_on_gpu(p_table):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_bench_batches_and_merge_rounds_match_t_n(world, p_table):
+    """bench.py's N-GPU decomposition (batch_bounds -> one clustering pass per batch -> ids-only
+    merge rounds on rank 0), run here batch after batch on one GPU, gives the clusters of the
+    --t N path (oracle, pinned to the reference's --t 4 / --t 8 golden vectors)."""
+    import bench
+    from ngspeciesid_b200 import engine as E
+    ra = oc.read_array_from_sorted(oc.sort_stage(scenario_reads("synth2k"), 13))
+    p_emp = oc.load_p_emp(p_table, 13, 20)
+    exp_cl, _exp_rp = oc.parallel_clustering(ra, p_emp, oc.default_args(nr_cores=world))
+    idx_of = {r[2]: r[0] for r in ra}
+    expected = sorted(sorted(idx_of[a] for a in accs) for accs in exp_cl.values())
+
+    seq = np.frombuffer("".join(r[3] for r in ra).encode(), dtype=np.uint8)
+    qual = np.frombuffer("".join(r[4] for r in ra).encode(), dtype=np.uint8)
+    off = np.zeros(len(ra) + 1, dtype=np.int64)
+    np.cumsum([len(r[3]) for r in ra], out=off[1:])
+    acc = [r[2] for r in ra]
+    params = {"max_gap": E.max_gap_table(p_emp, 0.1)}
+    bounds = bench.batch_bounds(np.diff(off), world)
+    eng, eng2 = E.Engine(0), E.Engine(0)
+    try:
+        rep_of, gathered = {}, []
+        for b in range(world):
+            lo, hi = bounds[b], bounds[b + 1]
+            s_seq, s_qual, s_off = bench.slice_reads(seq, qual, off, lo, hi)
+            eng.upload(s_seq, s_qual, s_off)
+            eng.minimizers(13, 20)
+            eng.quality_stats()
+            assign, _via, _st = eng.cluster(13, 20, params["max_gap"], np.arange(hi - lo, dtype=np.int32),
+                                            E.accession_ranks(acc[lo:hi]))
+            for i, a in enumerate(assign):
+                if a != -2:
+                    rep_of[lo + i] = lo + i if a == -1 else lo + int(a)
+            gathered.append([lo + i for i in np.nonzero(assign == -1)[0]])
+        merges, final = bench.merge_representatives(eng2, seq, qual, off, acc, gathered, params)
+    finally:
+        eng.close(); eng2.close()
+
+    def root(r):
+        while r in merges:
+            r = merges[r]
+        return r
+    groups = {}
+    for g, r in rep_of.items():
+        groups.setdefault(root(r), []).append(g)
+    assert sorted(groups) == sorted(final)
+    assert sorted(sorted(v) for v in groups.values()) == expected
+
+
 def _mixed_reads(n, seed):
     """Species reads plus a large share of unrelated junk reads, so that new representatives,
     chains of tentative representatives and re-evaluations all occur."""
