@@ -542,7 +542,9 @@ def run_reference(args):
     n_total = args.reads * max(1, world)
     seq, qual, offsets, acc = make_workload(n_total, args.seed + max(1, world) - 1)
     p_emp = p_minimizers_shared.p_emp_for(K, W)
-    per_core = args.ref_reads_per_core
+    # bounded sample: about two minutes of CPU work for the whole run whatever --steps is
+    # (the port clusters ~300 reads/s per core)
+    per_core = min(args.ref_reads_per_core, max(100, int(120 * 300 / max(1, args.steps))))
     ns = min(n_total, per_core * cores)
     ra = read_array(seq, qual, offsets, acc, 0, ns)
     a = oc.default_args(nr_cores=cores)
@@ -596,7 +598,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
