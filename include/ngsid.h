@@ -51,7 +51,9 @@ float ngsid_phase_ms(ngsid_ctx *ctx, int which);
  * every (k, w); 2 the older thread-per-read ring kernel instead of the stream kernel.
  * option 2: value != 0 selects the trace-free payload variant of K4.
  * option 3 selects the shape of the K4 DP kernel: 0 (default) per launch by the number of pairs,
- * 1 always one warp per pair, 2 always one thread block per pair (pipelined strips).            */
+ * 1 always one warp per pair, 2 always one thread block per pair (pipelined strips).
+ * option 4 selects the K4 traceback kernel: 0 (default) per launch by the number of pairs,
+ * 1 always one warp per pair, 2 always one thread per pair (no window breaking points).         */
 int ngsid_set_option(ngsid_ctx *ctx, int option, int value);
 
 /* ---- read upload ---------------------------------------------------------------------------

@@ -368,3 +368,73 @@ k4t_traceback_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
         out_win[pr * K4T_MAXWIN + lane] = (lane < nwin) ? mywin : x;
     }
 }
+
+// ---- traceback: one THREAD per pair (bulk launches) ---------------------------------------------
+// The warp kernel above spends a whole warp on one sequential walk (~65 warp-instructions per step,
+// 15 % of K4's instructions); with tens of thousands of pairs per launch the walks are better run
+// 32 to a warp: every step is one dependent 4-byte load of the trace word (L2 / HBM latency, hidden
+// by the number of pairs) plus the same state machine. Same results as the warp kernel (tested on
+// the same pairs); no window breaking points (consensus uses the warp kernel).
+__global__ void __launch_bounds__(128)
+k4t_traceback_thread_kernel(K4TSeqs Q, const int32_t *__restrict__ pa,
+                            const int32_t *__restrict__ pb, const int32_t *__restrict__ pm, int stride,
+                            int64_t pair0, int64_t n_pairs, int k, const uint32_t *__restrict__ trace,
+                            size_t slot_words, const K4TEnd *__restrict__ ends,
+                            int32_t *__restrict__ out_count, int32_t *__restrict__ out_score,
+                            int32_t *__restrict__ out_match, int32_t *__restrict__ out_cols)
+{
+    const int64_t sl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl >= n_pairs) return;
+    const int64_t pr = pair0 + sl;
+    const int ra = pa[pr * stride], rb = pb[pr * stride];
+    const int n1 = Q.len(ra), n2 = Q.len(rb);
+    const uint8_t *s1 = Q.ptr(ra), *s2 = Q.ptr(rb);
+    const K4TEnd e = ends[sl];
+    const uint32_t *tr = trace + (size_t)sl * slot_words;
+    const size_t nsteps = (size_t)n2 + 31;
+    K4TStat S;
+    S.hist = 0; S.ncol = 0; S.cnt = 0; S.k = k; S.m = pm ? pm[pr * stride] : 1;
+    S.hm = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+    int n_match = 0, n_cols = 0;
+    const int trailing = (n1 - 1 - e.end_i) + (n2 - 1 - e.end_j);
+    for (int t = 0; t < trailing; ++t) S.push(0u);
+    n_cols += trailing;
+    int i = e.end_i, j = e.end_j, state = 0;
+    size_t cur_idx = (size_t)-1;
+    uint32_t word = 0;
+    while (i >= 0 && j >= 0) {
+        const int strip = (i & 255) >> 3;
+        const size_t idx = ((size_t)(i >> 8) * nsteps + (size_t)(j + strip)) * 32 + (size_t)strip;
+        if (idx != cur_idx) { word = __ldg(tr + idx); cur_idx = idx; }
+        const uint32_t nib = (word >> (4 * (i & 7))) & 15u;
+        if (state == 0) {
+            if ((nib & 3u) == 3u) state = 3;
+            else if (nib & 1u) state = 2;
+            else {
+                const uint32_t mt = (__ldg(s1 + i) == __ldg(s2 + j)) ? 1u : 0u;
+                S.push(mt);
+                n_match += (int)mt;
+                n_cols++;
+                --i; --j;
+            }
+        } else if (state == 2) {
+            S.push(0u); n_cols++;
+            if (nib & 4u) state = 0;
+            --j;
+        } else {
+            S.push(0u); n_cols++;
+            if (nib & 8u) state = 0;
+            --i;
+        }
+    }
+    const int leading = (i + 1) + (j + 1);
+    for (int t = 0; t < leading; ++t) S.push(0u);
+    n_cols += leading;
+    int cnt = S.cnt;
+    if (n_cols < k) cnt = (__popc(S.hist) >= S.m) ? 1 : 0;
+    if (out_count) out_count[pr] = cnt;
+    if (out_score) out_score[pr] = e.score;
+    if (out_match) out_match[pr] = n_match;
+    if (out_cols) out_cols[pr] = n_cols;
+}
+

@@ -75,6 +75,11 @@ extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
         ctx->k4_shape = value;
         return NGSID_OK;
     }
+    if (option == 4) {
+        if (value < 0 || value > 2) return fail(ctx, NGSID_EINVAL, "option 4 takes 0, 1 or 2");
+        ctx->k4_tb = value;
+        return NGSID_OK;
+    }
     return fail(ctx, NGSID_EINVAL, "unknown option");
 }
 
@@ -484,7 +489,11 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
     CUDA_TRY(ctx, cudaFuncSetAttribute(k4t_traceback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
 
     const size_t slot_words = k4t_trace_words(max_n1, max_n2);
-    const size_t budget = (size_t)4 << 30;
+    // trace arena: 4 GB, 16 GB for bulk launches (the thread-per-pair traceback is latency bound:
+    // one launch over 50 k pairs costs what one over 13 k does)
+    static const int64_t tb_thread_min = getenv("NGSID_K4_TB_THREAD_MIN") ? atoll(getenv("NGSID_K4_TB_THREAD_MIN")) : 12288;
+    const bool thread_tb_ok = out_win == nullptr && ctx->k4_tb != 1;
+    const size_t budget = (thread_tb_ok && n_pairs > 2 * tb_thread_min) ? (size_t)16 << 30 : (size_t)4 << 30;
     int64_t slots = (int64_t)std::max<size_t>(1, budget / (slot_words * 4));
     slots = std::min<int64_t>(slots, n_pairs);
     CUDA_TRY(ctx, ctx->d_trace.ensure((size_t)slots * slot_words * 4));
@@ -510,9 +519,14 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
                                                                           ctx->d_ends.as<K4TEnd>());
         }
         KERNEL_CHECK(ctx);
-        k4t_traceback_kernel<<<(unsigned)((c + tb_wpb - 1) / tb_wpb), tb_wpb * 32, tb_smem, ctx->stream>>>(
-            Q, pa, pb, pm, stride, p0, c, k, ctx->d_trace.as<uint32_t>(), slot_words, ctx->d_ends.as<K4TEnd>(),
-            out_count, out_score, out_match, out_cols, out_win, window, ncap);
+        if (thread_tb_ok && (ctx->k4_tb == 2 || c >= tb_thread_min))
+            k4t_traceback_thread_kernel<<<(unsigned)((c + 127) / 128), 128, 0, ctx->stream>>>(
+                Q, pa, pb, pm, stride, p0, c, k, ctx->d_trace.as<uint32_t>(), slot_words, ctx->d_ends.as<K4TEnd>(),
+                out_count, out_score, out_match, out_cols);
+        else
+            k4t_traceback_kernel<<<(unsigned)((c + tb_wpb - 1) / tb_wpb), tb_wpb * 32, tb_smem, ctx->stream>>>(
+                Q, pa, pb, pm, stride, p0, c, k, ctx->d_trace.as<uint32_t>(), slot_words, ctx->d_ends.as<K4TEnd>(),
+                out_count, out_score, out_match, out_cols, out_win, window, ncap);
         KERNEL_CHECK(ctx);
     }
     return NGSID_OK;

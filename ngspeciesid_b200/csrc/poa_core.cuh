@@ -139,7 +139,11 @@ POA_HD void poa_topo_sort(PoaGraph &G)
         while (sp > 0) {
             const int v = G.stack[sp - 1];
             bool ok = true;
-            if (G.mark[v] != 2) {
+            const int mv = G.mark[v];
+            // mark 1 = v has pushed its unfinished predecessors / aligned nodes before and is on top
+            // again: everything above it has been popped, i.e. finished (the graph is acyclic, aligned
+            // nodes included), so the second scan of spoa's loop would find nothing -- skip it
+            if (mv == 0) {
                 for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) {
                     const int u = G.e_from[e];
                     if (G.mark[u] != 2) {
@@ -156,6 +160,8 @@ POA_HD void poa_topo_sort(PoaGraph &G)
                         }
                     }
                 }
+            }
+            if (mv != 2) {
                 if (ok) {
                     G.mark[v] = 2;
                     if (G.check[v]) {

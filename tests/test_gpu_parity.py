@@ -145,6 +145,30 @@ def test_k4_block_align_random_pairs(eng, payload_kernel, shape):
         eng.set_option(3, 0)
 
 
+@pytest.mark.parametrize("shape", [0, 1])
+def test_k4_thread_per_pair_traceback(eng, shape):
+    """The bulk traceback kernel (one thread per pair, option 4 = 2) against the oracle on the same
+    random pairs as the warp kernel, and against the warp kernel on scores / identity columns."""
+    eng.set_option(4, 2)
+    eng.set_option(3, shape)
+    try:
+        _k4_random_pairs(eng)
+        rng = np.random.default_rng(9)
+        reads = ["".join(rng.choice(list("ACGT"), size=int(n))) for n in rng.integers(1, 900, size=60)]
+        reads += [reads[3][:200] + reads[4][50:], reads[5] * 2]
+        eng.upload_records([(s, "5" * len(s)) for s in reads])
+        A = [int(x) for x in rng.integers(0, len(reads), size=300)]
+        B = [int(x) for x in rng.integers(0, len(reads), size=300)]
+        got = eng.sg_align_paths(A, B, [3] * len(A))
+        eng.set_option(4, 1)
+        exp = eng.sg_align_paths(A, B, [3] * len(A))
+        for g, e in zip(got, exp):
+            assert (np.asarray(g) == np.asarray(e)).all()
+    finally:
+        eng.set_option(4, 0)
+        eng.set_option(3, 0)
+
+
 @pytest.mark.parametrize("shape", [1, 2])
 def test_k4_paths_identity_and_windows(eng, shape):
     """Score, identity and window breaking points against the oracle's expanded CIGAR."""
