@@ -165,28 +165,63 @@ def run_spoa(reads, spoa_out_file, spoa_path):
     return cons[0]
 
 
+def _racon_batch(jobs, racon_iter):
+    """jobs: [(reads fastq, centre fasta, outfolder)]. All centres are polished together: one
+    upload, and per iteration one alignment launch and one window-POA launch over every centre.
+    The jobs are independent, so every centre gets what a call of its own would give it."""
+    eng = _engine.get_engine()
+    flat, lists, rc_lists, names, targets = [], [], [], [], []
+    for reads_to_center, center_file, _out in jobs:
+        recs = _read_fastq(reads_to_center)
+        with open(center_file) as f:
+            lines = f.readlines()
+        names.append(lines[0].strip()[1:])
+        targets.append(lines[1].strip())
+        fwd = [(s, q) for _a, s, q in recs]
+        lists.append(list(range(len(flat), len(flat) + len(fwd))))
+        flat.extend(fwd)
+    n_fwd = len(flat)
+    for li in lists:                              # reverse complements behind all forward reads
+        rc_lists.append([n_fwd + i for i in li])
+    flat.extend([(reverse_complement(s), q[::-1]) for s, q in flat[:n_fwd]])
+    eng.upload_records(flat)
+    logs = [open(os.path.join(out, "stdout.txt"), "w") for _r, _c, out in jobs]
+    try:
+        for i in range(racon_iter):
+            targets = polish_round_batch(eng, targets, lists, rc_lists)
+            for (_r, _c, out), name, target, li, log in zip(jobs, names, targets, lists, logs):
+                open(os.path.join(out, "read_alignments_it_{0}.paf".format(i)), "w").close()
+                with open(os.path.join(out, "racon_polished_it_{0}.fasta".format(i)), "w") as f:
+                    f.write(">{0} LN:i:{1} RC:i:{2} XC:f:1.000000\n{3}\n".format(name, len(target), len(li), target))
+                log.write("iteration {0}: {1} bases\n".format(i, len(target)))
+        for (_r, _c, out), name, target, li in zip(jobs, names, targets, lists):
+            with open(os.path.join(out, "consensus.fasta"), "w") as f:
+                f.write(">{0} LN:i:{1} RC:i:{2} XC:f:1.000000\n{3}\n".format(name, len(target), len(li), target))
+    finally:
+        for log in logs:
+            log.close()
+    return targets
+
+
 def run_racon(reads_to_center, center_file, outfolder, cores, racon_iter):
     """Reference: modules/consensus.py:107-126. Writes racon_polished_it_<i>.fasta per iteration and
     consensus.fasta (2-line FASTA) into `outfolder`; reads of either strand are used in the
     orientation that aligns better to the centre (what minimap2 decides in the reference)."""
-    recs = _read_fastq(reads_to_center)
-    with open(center_file) as f:
-        lines = f.readlines()
-    name, target = lines[0].strip()[1:], lines[1].strip()
-    eng = _engine.get_engine()
-    fwd = [(s, q) for _a, s, q in recs]
-    rc = [(reverse_complement(s), q[::-1]) for s, q in fwd]
-    eng.upload_records(fwd + rc)
-    n = len(fwd)
-    with open(os.path.join(outfolder, "stdout.txt"), "w") as log:
-        for i in range(racon_iter):
-            target = polish_round_batch(eng, [target], [list(range(n))], [list(range(n, 2 * n))])[0]
-            open(os.path.join(outfolder, "read_alignments_it_{0}.paf".format(i)), "w").close()
-            with open(os.path.join(outfolder, "racon_polished_it_{0}.fasta".format(i)), "w") as f:
-                f.write(">{0} LN:i:{1} RC:i:{2} XC:f:1.000000\n{3}\n".format(name, len(target), n, target))
-            log.write("iteration {0}: {1} bases\n".format(i, len(target)))
-        with open(os.path.join(outfolder, "consensus.fasta"), "w") as f:
-            f.write(">{0} LN:i:{1} RC:i:{2} XC:f:1.000000\n{3}\n".format(name, len(target), n, target))
+    _racon_batch([(reads_to_center, center_file, outfolder)], racon_iter)
+
+
+def run_medaka(reads_to_center, center_file, outfolder, cores, medaka_model, outfastq=False):
+    """Reference: modules/consensus.py:94-104. medaka is a neural polisher outside this
+    implementation: like the reference this shells out to the
+    `medaka_consensus` executable, which has to be installed."""
+    import subprocess
+    with open(os.path.join(outfolder, "stdout.txt"), "w") as out, open(os.path.join(outfolder, "stderr.txt"), "w") as err:
+        cmd = ["medaka_consensus", "-i", reads_to_center, "-d", center_file, "-o", outfolder, "-t", cores]
+        if medaka_model:
+            cmd += ["-m", medaka_model]
+        if outfastq:
+            cmd += ["-q"]
+        subprocess.check_call(cmd, stdout=out, stderr=err)
 
 
 def highest_aln_identity(seq, seq2):
@@ -273,13 +308,17 @@ def form_draft_consensus(clusters, representatives, sorted_reads_fastq_file, wor
 
 
 def polish_sequences(centers, args):
-    """Reference: modules/consensus.py:186-246 (racon branch; --medaka is not provided here)."""
-    if getattr(args, "medaka", False):
-        raise NotImplementedError("medaka polishing is outside this implementation (use --racon)")
-    for folder in glob.glob(os.path.join(args.outfolder, "racon_cl_id_*")):
+    """Reference: modules/consensus.py:186-246: same files (consensus_reference_<id>.fasta,
+    reads_to_consensus_<id>.fastq, racon_cl_id_<id>/ or medaka_cl_id_<id>/) and the same update of
+    centers[i][2]. With --racon all centres are polished in one batch (the centres are
+    independent); --medaka shells out per centre like the reference."""
+    medaka = bool(getattr(args, "medaka", False))
+    prefix = "medaka_cl_id_" if medaka else "racon_cl_id_"
+    for folder in glob.glob(os.path.join(args.outfolder, prefix + "*")):
         shutil.rmtree(folder)
     for file in glob.glob(os.path.join(args.outfolder, "consensus_reference_*")):
         os.remove(file)
+    jobs = []
     for i, (nr_reads_in_cluster, c_id, center, all_reads) in enumerate(centers):
         spoa_center_file = os.path.join(args.outfolder, "consensus_reference_{0}.fasta".format(c_id))
         with open(spoa_center_file, "w") as f:
@@ -290,10 +329,23 @@ def polish_sequences(centers, args):
                 reads = {acc: (seq, qual) for acc, seq, qual in _read_fastq(fasta_file)}
                 for acc, (seq, qual) in reads.items():
                     f.write("@{0}\n{1}\n{2}\n{3}\n".format(acc.split()[0], seq, "+", qual))
-        if args.racon:
-            polishing_outfolder = os.path.join(args.outfolder, "racon_cl_id_{0}".format(c_id))
+        polishing_outfolder = os.path.join(args.outfolder, "{0}{1}".format(prefix, c_id))
+        if medaka:
             help_functions.mkdir_p(polishing_outfolder)
-            run_racon(all_reads_file, spoa_center_file, polishing_outfolder, "1", args.racon_iter)
+            run_medaka(all_reads_file, spoa_center_file, polishing_outfolder, "1", args.medaka_model,
+                       outfastq=getattr(args, "medaka_fastq", False))
+            for name in ("consensus.fasta", "consensus.fastq"):
+                if os.path.isfile(os.path.join(polishing_outfolder, name)):
+                    with open(os.path.join(polishing_outfolder, name), "r") as cf:
+                        centers[i][2] = cf.readlines()[1].strip()
+                    break
+            assert centers[i][2], "Medaka consensus sequence not found"
+        elif args.racon:
+            help_functions.mkdir_p(polishing_outfolder)
+            jobs.append((all_reads_file, spoa_center_file, polishing_outfolder, i))
+    if jobs:
+        _racon_batch([j[:3] for j in jobs], args.racon_iter)
+        for _r, _c, polishing_outfolder, i in jobs:
             with open(os.path.join(polishing_outfolder, "consensus.fasta"), "r") as cf:
                 centers[i][2] = cf.readlines()[1].strip()
     return centers

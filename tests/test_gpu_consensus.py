@@ -139,6 +139,52 @@ def test_run_spoa_and_run_racon_files(eng, tmp_path):
     assert os.path.exists(out / "racon_polished_it_1.fasta")
 
 
+def test_form_draft_consensus_and_polish_sequences_files(eng, tmp_path):
+    """The two drivers with the reference's file layout (consensus.py:249-278, :186-246): clusters
+    above the abundance cut-off get a draft (all in one batch) and are polished (all in one batch);
+    every centre must equal what the oracle computes for it alone, and the files must be there."""
+    from types import SimpleNamespace
+    from ngspeciesid_b200.modules import consensus as C
+    rs, groups, tpl = species_reads(90, 3, 53, 380, 440)
+    sorted_fq = tmp_path / "sorted.fastq"
+    accs = []
+    with open(sorted_fq, "w") as f:
+        for i in range(len(rs)):
+            s, q = rs.read(i)
+            accs.append("%s_%d.5" % (rs.name(i), 1000 - i))
+            f.write("@%s\n%s\n+\n%s\n" % (accs[-1], s, q))
+    clusters, reps = {}, {}
+    for (sp, st), idx in groups.items():
+        c_id = idx[0]
+        clusters[c_id] = [accs[i] for i in idx]
+        reps[c_id] = (c_id, 0, accs[c_id], "", "", float(1000 - c_id))
+    clusters[10 ** 6] = ["lonely"]                                   # a singleton: no consensus
+    reps[10 ** 6] = (10 ** 6, 0, "lonely", "", "", 1.0)
+    work = tmp_path / "work"
+    os.makedirs(work)
+    args = SimpleNamespace(outfolder=str(tmp_path), max_seqs_for_consensus=12, racon=True, racon_iter=2, medaka=False, device=0)
+    big = sorted(clusters.items(), key=lambda x: (len(x[1]), reps[x[0]][5]), reverse=True)
+    cutoff = len(big[2][1])                                          # the three largest clusters pass
+    centers = C.form_draft_consensus(clusters, reps, str(sorted_fq), str(work), cutoff, args)
+    expect_ids = [c for c, a in big if len(a) >= cutoff]
+    assert [c[1] for c in centers] == expect_ids
+    idx_of = {a: i for i, a in enumerate(accs)}
+    drafts = {}
+    for n, c_id, cons, path in centers:
+        used = [rs.read(idx_of[a]) for a in clusters[c_id][:12]]
+        assert n == len(clusters[c_id]) and os.path.exists(path)
+        assert cons == co.spoa_consensus(used)
+        drafts[c_id] = (cons, used)
+    out = C.polish_sequences([list(c[:3]) + [[c[3]]] for c in centers], args)
+    for n, c_id, cons, _paths in out:
+        d, used = drafts[c_id]
+        assert cons == co.racon_polish(d, used, 2, both_strands=True)
+        assert open(tmp_path / ("racon_cl_id_%d" % c_id) / "consensus.fasta").readlines()[1].strip() == cons
+        assert open(tmp_path / ("consensus_reference_%d.fasta" % c_id)).readline().startswith(
+            ">consensus_cl_id_%d_total_supporting_reads_%d" % (c_id, n))
+        assert os.path.exists(tmp_path / ("reads_to_consensus_%d.fastq" % c_id))
+
+
 def test_highest_aln_identity(eng):
     from ngspeciesid_b200.modules import consensus as C
     rng = np.random.default_rng(3)
