@@ -35,10 +35,7 @@ K, W = 13, 20
 
 
 # ------------------------------------------------------------------------------------ workload
-def vector_scores(qual, offsets, k):
-    """Expected number of error-free k-mers per read (the reference's sort key,
-    get_sorted_fastq_for_cluster.py:23-33,150-152), vectorised with log-sums; used only to put the
-    synthetic reads in the order the reference's sort stage would."""
+def _vector_scores_block(qual, offsets, k):
     p = np.minimum(10.0 ** (-(qual.astype(np.float64) - 33.0) / 10.0), 0.79433)
     lg = np.log1p(-p)
     cs = np.concatenate([[0.0], np.cumsum(lg)])
@@ -55,6 +52,19 @@ def vector_scores(qual, offsets, k):
     hi = np.minimum(offsets[1:], len(win))
     lo = np.minimum(offsets[:-1], len(win))
     return ce[hi] - ce[lo]
+
+
+def vector_scores(qual, offsets, k, block=20000):
+    """Expected number of error-free k-mers per read (the reference's sort key,
+    get_sorted_fastq_for_cluster.py:23-33,150-152), vectorised with log-sums; used only to put the
+    synthetic reads in the order the reference's sort stage would. Blocks of reads keep the float64
+    temporaries small (a 900 k-read pool would otherwise need ~40 GB per process)."""
+    n = len(offsets) - 1
+    out = np.zeros(n)
+    for a in range(0, n, block):
+        b = min(n, a + block)
+        out[a:b] = _vector_scores_block(qual[offsets[a]:offsets[b]], offsets[a:b + 1] - offsets[a], k)
+    return out
 
 
 def make_workload(n_reads, seed, cache=True):
@@ -85,7 +95,9 @@ def make_workload(n_reads, seed, cache=True):
     acc = ["read%d species=%d strand=%s_%r" % (i, rs.species[i], "+-"[rs.strand[i]], float(s))
            for i, s in zip(order, score_sorted)]
     if cache:
-        np.savez(path, seq=seq, qual=qual, offsets=new_off, acc=np.array([a.encode() for a in acc]))
+        tmp = "%s.%d.tmp.npz" % (path, os.getpid())          # atomic: other ranks may be polling for it
+        np.savez(tmp, seq=seq, qual=qual, offsets=new_off, acc=np.array([a.encode() for a in acc]))
+        os.replace(tmp, path)
     return seq, qual, new_off, acc
 
 
@@ -237,6 +249,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n_total = args.reads * world
+    if world > 1:
+        # rank 0 generates (or finds) the pool and leaves it in the cache; the others load it
+        if rank == 0:
+            make_workload(n_total, args.seed + world - 1)
+        dist.barrier()
     seq, qual, offsets, acc = make_workload(n_total, args.seed + world - 1)
     p_emp = p_minimizers_shared.p_emp_for(K, W)
     params = {"max_gap": E.max_gap_table(p_emp, 0.1)}
