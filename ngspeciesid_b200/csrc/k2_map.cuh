@@ -176,6 +176,7 @@ __device__ __forceinline__ bool key_greater(uint32_t n1, uint32_t s1, uint32_t a
 }
 
 #define VISITED_BIT 0x80000000u
+#define K2_SMEM_SLOTS 192      // representatives up to which the map kernel counts hits in shared memory
 
 __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
 {
@@ -184,9 +185,19 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
     const int warps_per_block = blockDim.x >> 5;
     const int gwarp = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * warps_per_block;
-    uint32_t *cnt = A.scratch + (size_t)gwarp * 3 * A.scap;
-    uint32_t *spos = cnt + A.scap;
-    uint32_t *touched = spos + A.scap;
+    // per-warp hit counters: in shared memory while the table holds few representatives (amplicon
+    // data: tens), so that the counting atomics of pass 1 do not pay an L2 round trip per posting
+    // node; in the global scratch otherwise
+    __shared__ uint32_t s_scr[8][3 * K2_SMEM_SLOTS];
+    const bool scr_shared = A.n_slots <= K2_SMEM_SLOTS;
+    const int scr_stride = scr_shared ? K2_SMEM_SLOTS : A.scap;
+    uint32_t *cnt = scr_shared ? s_scr[threadIdx.x >> 5] : A.scratch + (size_t)gwarp * 3 * A.scap;
+    uint32_t *spos = cnt + scr_stride;
+    uint32_t *touched = spos + scr_stride;
+    if (scr_shared) {
+        for (int x = (int)lane; x < 3 * K2_SMEM_SLOTS; x += 32) cnt[x] = 0u;
+        __syncwarp();
+    }
     __shared__ uint32_t s_ntouched[8];
     uint32_t *ntouched = &s_ntouched[threadIdx.x >> 5];
 
