@@ -294,6 +294,14 @@ def _run_scenario(tag, p_table):
     assert origins == [o[:4] for o in g["origins"]]
     for rep, _a in out:
         assert reps[rep][7] == oc.hpol_compress(reps[rep][3])[0]
+    # the two output files, byte for byte what the reference wrote for this scenario
+    import tempfile
+    from ngspeciesid_b200.modules import cluster_output
+    with tempfile.TemporaryDirectory() as folder:
+        cluster_output.write_cluster_tsvs(clusters, reps, folder)
+        for name, key in (("final_clusters.tsv", "final_clusters_sha1"), ("final_cluster_origins.tsv", "final_cluster_origins_sha1")):
+            with open(os.path.join(folder, name), "rb") as f:
+                assert hashlib.sha1(f.read()).hexdigest() == g[key], name
 
 
 @pytest.mark.parametrize("tag", ["h1_t1", "h1_t4", "h1_sym_t1", "supp1k_t1", "supp1k_t8",

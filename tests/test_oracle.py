@@ -1,6 +1,7 @@
 """The CPU oracle (oracle/) against the golden vectors produced by the reference itself
 (tests/golden/make_golden.py). CPU only."""
 import hashlib
+import os
 
 import pytest
 
@@ -42,7 +43,17 @@ def test_primitives(idx):
     assert n == len(g["reads"])
 
 
-def run_oracle_scenario(tag, p_table):
+def check_tsv_files(clusters, reps, g, folder):
+    """The two output files against the SHA-1 of the files the reference wrote for this scenario."""
+    from ngspeciesid_b200.modules import cluster_output
+    n_big, n_all = cluster_output.write_cluster_tsvs(clusters, reps, folder)
+    assert n_all == len(clusters) and n_big == sum(1 for a in clusters.values() if len(a) > 1)
+    for name, key in (("final_clusters.tsv", "final_clusters_sha1"), ("final_cluster_origins.tsv", "final_cluster_origins_sha1")):
+        with open(os.path.join(folder, name), "rb") as f:
+            assert hashlib.sha1(f.read()).hexdigest() == g[key], name
+
+
+def run_oracle_scenario(tag, p_table, tmp_path=None):
     g = load_golden("clusters_%s.json.gz" % tag)
     args = scenario_args(g)
     recs = scenario_reads(tag)
@@ -63,9 +74,11 @@ def run_oracle_scenario(tag, p_table):
     origins = [[i, rep, repr(reps[rep][5]), repr(reps[rep][6])]
                for i, (rep, _a) in enumerate(oc.output_order(clusters, reps))]
     assert origins == [o[:4] for o in g["origins"]]
+    if tmp_path is not None:
+        check_tsv_files(clusters, reps, g, str(tmp_path))
 
 
 @pytest.mark.parametrize("tag", ["h1_t1", "h1_t4", "h1_sym_t1", "supp1k_t1", "supp1k_t8",
                                  "synth2k_t1", "synth2k_t8", "synthpb_t1"])
-def test_pipeline_matches_reference(tag, p_table):
-    run_oracle_scenario(tag, p_table)
+def test_pipeline_matches_reference(tag, p_table, tmp_path):
+    run_oracle_scenario(tag, p_table, tmp_path)
