@@ -5,8 +5,9 @@ as there); the batches of a round run one after the other on the GPU instead of 
 pool -- they are independent, so the result is the same.
 """
 import math
+import os
 
-from . import cluster
+from . import cluster, help_functions
 
 
 def batch_list(lst, nr_cores=1, batch_type="nr_reads", merge_consecutive=False):
@@ -44,6 +45,30 @@ def batch_list(lst, nr_cores=1, batch_type="nr_reads", merge_consecutive=False):
     yield cur
 
 
+def print_intermediate_results(clusters, cluster_seq_origin, args, iter_nr):
+    """Reference: modules/parallelize.py:83-104: the snapshot of a merge round,
+    <outfolder>/<iter_nr>/pre_clusters.csv (cluster id, read name without its score suffix; clusters
+    by size descending, members in list order) and cluster_origins.csv (one line per
+    representative). Nothing reads these files back, in the reference or here."""
+    path = args.outfolder + "/{0}".format(iter_nr)
+    help_functions.mkdir_p(path)
+    ordered = sorted(clusters.items(), key=lambda x: len(x[1]), reverse=True)
+    with open(os.path.join(path, "pre_clusters.csv"), "w") as f:
+        for c_id, accs in ordered:
+            for r_acc in accs:
+                f.write("{0}\t{1}\n".format(c_id, "_".join(r_acc.split("_")[:-1])))
+    with open(os.path.join(path, "cluster_origins.csv"), "w") as f:
+        for c_id, _accs in ordered:
+            read_cl_id, _b, acc, seq, qual, score, error_rate, _comp = cluster_seq_origin[c_id]
+            f.write("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\n".format(read_cl_id, acc, seq, qual, score, error_rate))
+
+
+def _snapshot(all_cl, all_rp, args, it):
+    # the reference always has an output folder; library callers (and the tests) may not
+    if getattr(args, "outfolder", None):
+        print_intermediate_results(all_cl, all_rp, args, it)
+
+
 def parallel_clustering(read_array, p_emp_probs, args):
     """Reference: modules/parallelize.py:107-217 -> (clusters, representatives)."""
     batches = list(batch_list(read_array, args.nr_cores, batch_type=args.batch_type))
@@ -51,6 +76,7 @@ def parallel_clustering(read_array, p_emp_probs, args):
     cl = [{r[0]: [r[2]] for r in b} for b in batches]
     rp = [{r[0]: tuple(r) for r in b} for b in batches]
     db = [{} for _ in batches]
+    it = 1
     while True:
         if len(batches) == 1:
             res = cluster.reads_to_clusters(cl[0], rp[0], batches[0], p_emp_probs, db[0], 1, args)
@@ -66,6 +92,8 @@ def parallel_clustering(read_array, p_emp_probs, args):
                       sorted(all_rp.items(), key=lambda x: x[1][5], reverse=True)]
         if num == 1:
             return all_cl, all_rp
+        _snapshot(all_cl, all_rp, args, it)
+        it += 1
         batches = list(batch_list(read_array, num, batch_type=args.batch_type, merge_consecutive=True))
         num = len(batches)
         cl, rp, db = [], [], []
@@ -98,6 +126,7 @@ def parallel_clustering_ranks(read_array, p_emp_probs, args, group=None, cluster
     cl = [{r[0]: [r[2]] for r in b} for b in batches]
     rp = [{r[0]: tuple(r) for r in b} for b in batches]
     db = [{} for _ in batches]
+    it = 1
     while True:
         if len(batches) == 1:
             # last round runs in one process in the reference too (parallelize.py:142-149)
@@ -122,6 +151,9 @@ def parallel_clustering_ranks(read_array, p_emp_probs, args, group=None, cluster
                       sorted(all_rp.items(), key=lambda x: x[1][5], reverse=True)]
         if num == 1:
             return all_cl, all_rp
+        if rank == 0:
+            _snapshot(all_cl, all_rp, args, it)
+        it += 1
         batches = list(batch_list(read_array, num, batch_type=args.batch_type, merge_consecutive=True))
         num = len(batches)
         cl, rp, db = [], [], []

@@ -22,6 +22,7 @@ def main():
     rank = dist.get_rank()
     g = load_golden("clusters_%s.json.gz" % tag)
     args = scenario_args(g)
+    args.outfolder = out_dir                      # rank 0 leaves the per-round snapshots there
     z = np.load(os.path.join(ROOT, "ngspeciesid_b200", "data", "p_shared_table.npz"))
     p_table = [(int(k), int(w), float(p), e1 / 100.0, e2 / 100.0)
                for k, w, p, e1, e2 in zip(z["k"], z["w"], z["p"], z["e1"], z["e2"])]

@@ -64,3 +64,17 @@ def test_batch_list_matches_oracle():
         assert list(parallelize.batch_list(reads, t, batch_type="nr_reads")) == oc.split_batches(reads, t, "nr_reads")
     tagged = [(r[0], 1 + (i * 4) // len(reads), r[2], r[3], r[4], r[5]) for i, r in enumerate(reads)]
     assert list(parallelize.batch_list(tagged, 4, merge_consecutive=True)) == oc.pair_batches(tagged)
+
+
+def test_round_snapshot_files_match_reference(tmp_path):
+    """parallelize.print_intermediate_results against the files the reference's own function wrote
+    for the same inputs (tests/golden/make_intermediate_golden.py)."""
+    import os
+    from types import SimpleNamespace
+    from conftest import load_golden
+    for c in load_golden("intermediate.json.gz"):
+        clusters = {int(k): v for k, v in c["clusters"].items()}
+        reps = {int(k): tuple(v) for k, v in c["reps"].items()}
+        parallelize.print_intermediate_results(clusters, reps, SimpleNamespace(outfolder=str(tmp_path)), c["it"])
+        for name, text in c["files"].items():
+            assert open(os.path.join(str(tmp_path), str(c["it"]), name)).read() == text

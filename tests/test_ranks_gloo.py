@@ -32,6 +32,16 @@ def test_rank_sharded_clustering_matches_reference(tag, world, tmp_path):
     assert res.returncode == 0, res.stdout[-3000:]
     g = load_golden("clusters_%s.json.gz" % tag)
     n_batches = int(g["args"][g["args"].index("--t") + 1])
+    # per-round snapshots of the --t N path (parallelize.py:83-104), written once (rank 0)
+    rounds = 0
+    while (n_batches >> rounds) > 1:
+        rounds += 1
+    for it in range(1, rounds + 1):
+        pre = open(os.path.join(str(tmp_path), str(it), "pre_clusters.csv")).read().splitlines()
+        org = open(os.path.join(str(tmp_path), str(it), "cluster_origins.csv")).read().splitlines()
+        assert len(pre) == sum(len(c) for c in g["clusters"])
+        assert len(org) == len(set(l.split("\t")[0] for l in pre))
+    assert not os.path.exists(os.path.join(str(tmp_path), str(rounds + 1)))
     for r in range(world):
         out = json.load(open(os.path.join(str(tmp_path), "rank%d.json" % r)))
         assert out["clusters"] == g["clusters"]
