@@ -13,7 +13,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std
 
 def sources():
     d = os.path.join(HERE, "csrc")
-    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(HERE, "..", "include", "ngsid.h")]
+    return ([os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh", ".h"))]
+            + [os.path.join(HERE, "..", "include", "ngsid.h")])
 
 
 def up_to_date():
@@ -32,7 +33,9 @@ def build_library(force=False, verbose=False):
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed for libngsid.so")
-    with open(os.path.join(HERE, "csrc", ".ptxas.log"), "w") as f:
+    logdir = os.path.join(HERE, "..", "build")          # git-ignored; the register / spill report of the last build
+    os.makedirs(logdir, exist_ok=True)
+    with open(os.path.join(logdir, "ptxas.log"), "w") as f:
         f.write(res.stdout)
     return OUT
 

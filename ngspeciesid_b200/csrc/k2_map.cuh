@@ -51,7 +51,8 @@ __device__ __forceinline__ int32_t table_lookup(const MapTable &t, uint32_t key)
 // ---- insert the minimizers of new representative slots [slot0, slot0 + n) ----------------------
 // One warp per slot. A k-mer occurring at several positions of the representative is inserted
 // once (the reference keeps a set of ids per k-mer, cluster.py:330-334).
-__global__ void k2_insert_kernel(MapTable t, int32_t *__restrict__ node_cursor,
+__global__ void k2_insert_kernel(MapTable t, int32_t *__restrict__ node_cursor, int32_t node_cap,
+                                 int32_t *__restrict__ err_flag,
                                  const int32_t *__restrict__ slot_read, int slot0, int n_slots,
                                  const Minimizer *__restrict__ mins,
                                  const int64_t *__restrict__ moff,
@@ -86,6 +87,7 @@ __global__ void k2_insert_kernel(MapTable t, int32_t *__restrict__ node_cursor,
             h = (h + 1) & t.cap_mask;
         }
         int32_t node = atomicAdd(node_cursor, 1);
+        if (node >= node_cap) { *err_flag = 3; continue; }      // host sizes the pool before the launch: never expected
         t.nodes[node].slot = slot;
         t.nodes[node].next = atomicExch(&t.heads[h], node);
     }
@@ -120,6 +122,10 @@ struct AlignRequest {
 };
 
 struct AlignCacheEntry { int32_t slot; int32_t passed; };   // slot < 0 = free
+// Results beyond the ACACHE_N inline entries of a read (more than ACACHE_N failed candidates over
+// all rounds of a pass: the reference tries every tied candidate, cluster.py:174-205) go to a
+// per-read chain of pool nodes.
+struct AlignCacheOvf { int32_t slot; int32_t passed; int32_t next; };
 
 struct MapArgs {
     MapTable table;
@@ -141,6 +147,9 @@ struct MapArgs {
     uint32_t *scratch;              // per warp: cnt[scap] | spos[scap] | touched[scap]
     int scap;
     AlignCacheEntry *acache;        // per position: ACACHE_N entries
+    const int32_t *aovf_head;       // per position: first overflow node or -1
+    int acache_inline;              // inline entries in use (ACACHE_N; tests lower it to reach the chain)
+    const AlignCacheOvf *aovf;
     int32_t *dec;                   // per position: representative read index / DEC_*
     uint8_t *via;                   // per position: 0 new, 1 map, 2 align
     AlignRequest *req;
@@ -154,6 +163,20 @@ struct MapArgs {
     int spec_lo, spec_hi, spec_cols;
     int spec_mode;                  // 1: this launch only emits the prefetch requests
 };
+
+// cached alignment result of (position, slot): -1 unknown, 0 failed, 1 passed
+__device__ __forceinline__ int acache_lookup(const MapArgs &A, int pos, int slot)
+{
+    const AlignCacheEntry *ac = A.acache + (size_t)pos * ACACHE_N;
+    int cached = -1;
+#pragma unroll
+    for (int e = 0; e < ACACHE_N; ++e)
+        if (ac[e].slot == slot) cached = ac[e].passed;
+    if (cached < 0 && ac[A.acache_inline - 1].slot >= 0)
+        for (int o = A.aovf_head[pos]; o >= 0; o = A.aovf[o].next)
+            if (A.aovf[o].slot == slot) { cached = A.aovf[o].passed; break; }
+    return cached;
+}
 
 // gap open penalty and match_id of a (read, representative) pair (cluster.py:185-198)
 __device__ __forceinline__ AlignRequest make_align_request(const MapArgs &A, int pos, int slot, int read, int k)
@@ -247,11 +270,10 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
             for (int d = 16; d > 0; d >>= 1) topc = max(topc, __shfl_xor_sync(NGSID_FULL_MASK, topc, d));
             const uint32_t thr = max(topc, (uint32_t)max(P.min_shared, 1));
             const int row = A.spec_u[pos - A.spec_lo];
-            const AlignCacheEntry *ac = A.acache + (size_t)pos * ACACHE_N;
             for (int t = lane; t < nt; t += 32) {
                 const int s = (int)touched[t];
                 bool ask = row >= 0 && s < A.spec_cols && cnt[s] >= thr;
-                for (int e = 0; e < ACACHE_N; ++e) if (ac[e].slot == s) ask = false;
+                if (ask && acache_lookup(A, pos, s) >= 0) ask = false;
                 if (ask && A.spec_mat[(size_t)row * A.spec_cols + s] < 0)
                     A.req[atomicAdd(A.req_n, 1)] = make_align_request(A, pos, s, read, P.k);
             }
@@ -341,7 +363,6 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
             // ---- alignment stage: candidates tied for the top hit count, rank order
             // (cluster.py:174-182); results of earlier K4 rounds come from the per-read cache.
             if (decision == DEC_NEW) {
-                AlignCacheEntry *ac = A.acache + (size_t)pos * ACACHE_N;
                 // clear the visited marks of the tied candidates, then walk them in order
                 for (int t = lane; t < nt; t += 32) {
                     int s = (int)touched[t];
@@ -368,9 +389,7 @@ __global__ void __launch_bounds__(256) k2_map_kernel(MapArgs A)
                     if (bslot < 0) break;                 // every tied candidate failed -> new
                     if (lane == 0) cnt[bslot] |= VISITED_BIT;
                     __syncwarp();
-                    int cached = -1;                      // -1 unknown, 0 failed, 1 passed
-                    for (int e = 0; e < ACACHE_N; ++e)
-                        if (ac[e].slot == bslot) cached = ac[e].passed;
+                    int cached = acache_lookup(A, pos, bslot);   // -1 unknown, 0 failed, 1 passed
                     if (cached < 0 && A.spec_u && pos >= A.spec_lo && pos < A.spec_hi && bslot < A.spec_cols) {
                         const int row = A.spec_u[pos - A.spec_lo];
                         if (row >= 0) cached = (int)A.spec_mat[(size_t)row * A.spec_cols + bslot];
@@ -401,6 +420,8 @@ __global__ void k2_apply_align_kernel(const AlignRequest *__restrict__ req, int 
                                       const int64_t *__restrict__ off,
                                       const DeviceClusterParams *__restrict__ params,
                                       AlignCacheEntry *__restrict__ acache,
+                                      int32_t *__restrict__ aovf_head, AlignCacheOvf *__restrict__ aovf,
+                                      int32_t *__restrict__ aovf_cursor, int32_t aovf_cap, int inline_n,
                                       int32_t *__restrict__ list_out, int32_t *err_flag)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,10 +435,17 @@ __global__ void k2_apply_align_kernel(const AlignRequest *__restrict__ req, int 
     int passed = ratio >= params->aligned_threshold ? 1 : 0;
     AlignCacheEntry *ac = acache + (size_t)rq.pos * ACACHE_N;
     int e = 0;
-    while (e < ACACHE_N && ac[e].slot >= 0) ++e;
-    if (e == ACACHE_N) { *err_flag = 2; return; }
-    ac[e].slot = rq.slot;
-    ac[e].passed = passed;
+    while (e < inline_n && ac[e].slot >= 0) ++e;
+    if (e == inline_n) {
+        // one request per read and round, so the chain of a position has a single writer
+        const int32_t o = atomicAdd(aovf_cursor, 1);
+        if (o >= aovf_cap) { *err_flag = 2; return; }
+        aovf[o].slot = rq.slot; aovf[o].passed = passed; aovf[o].next = aovf_head[rq.pos];
+        aovf_head[rq.pos] = o;
+    } else {
+        ac[e].slot = rq.slot;
+        ac[e].passed = passed;
+    }
     list_out[i] = rq.pos;
 }
 
@@ -439,10 +467,11 @@ __global__ void k2_apply_spec_kernel(const AlignRequest *__restrict__ req, int n
     spec_mat[(size_t)spec_u[rq.pos - spec_lo] * spec_cols + rq.slot] = ratio >= params->aligned_threshold ? 1 : 0;
 }
 
-__global__ void k2_fill_acache_kernel(AlignCacheEntry *ac, int64_t n)
+__global__ void k2_fill_acache_kernel(AlignCacheEntry *ac, int32_t *aovf_head, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { ac[i].slot = -1; ac[i].passed = 0; }
+    if (i < n / ACACHE_N) aovf_head[i] = -1;
 }
 
 __global__ void k2_iota_kernel(int32_t *list, int first, int n)

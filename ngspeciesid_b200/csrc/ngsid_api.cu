@@ -94,7 +94,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
                       &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
-                      &ctx->d_newslots, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+                      &ctx->d_newslots, &ctx->d_aovf, &ctx->d_aovf_head, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
     cudaEventDestroy(ctx->ev0);
@@ -807,6 +807,9 @@ struct ClusterRun {
     DevBuf keys_alt, heads_alt;        // spare pair for growth
     int64_t pairs_inserted = 0;
     int scap = 0, map_warps = 0, map_blocks = 0;
+    int aovf_cap = 0;                  // nodes of the alignment-result overflow pool
+    int slot_cap = 0;                  // entries of d_slot_read / d_slot_pos / d_slot_state
+    int64_t node_cap = 0;              // posting nodes of d_nodes
     DevBuf d_list2, d_err, d_spec_u, d_spec_mat;
     std::vector<int32_t> h_dec, h_spec_u;
     ngsid_cluster_stats st;
@@ -814,6 +817,7 @@ struct ClusterRun {
 
     int ensure_table(int64_t pairs_after);
     int ensure_scratch(int slots_after);
+    int ensure_slot_node_capacity(int64_t pairs_after);
     int push_slots();
     int set_state(int slot, uint8_t v);
     int insert_slots(int slot0, int count);
@@ -869,6 +873,30 @@ int ClusterRun::ensure_scratch(int slots_after)
     return NGSID_OK;
 }
 
+// Slots of tentative representatives that a surprise invalidates are never reused, and the reads
+// behind them are inserted again under new slots, so neither the slot arrays nor the posting nodes
+// are bounded by the number of reads: both grow here, contents kept.
+int ClusterRun::ensure_slot_node_capacity(int64_t pairs_after)
+{
+    if (n_slots > slot_cap) {
+        const int ncap = std::max(n_slots + 16, slot_cap * 2);
+        CUDA_TRY(ctx, ctx->d_slot_read.grow_keep((size_t)ncap * 4, (size_t)slots_on_device * 4, ctx->stream));
+        CUDA_TRY(ctx, ctx->d_slot_pos.grow_keep((size_t)ncap * 4, (size_t)slots_on_device * 4, ctx->stream));
+        CUDA_TRY(ctx, ctx->d_slot_state.grow_keep((size_t)ncap, (size_t)slots_on_device, ctx->stream));
+        slot_cap = ncap;
+        A.slot_read = ctx->d_slot_read.as<int32_t>();
+        A.slot_pos = ctx->d_slot_pos.as<int32_t>();
+        A.slot_state = ctx->d_slot_state.as<uint8_t>();
+    }
+    if (pairs_after + 1 > node_cap) {
+        const int64_t ncap = std::max<int64_t>(pairs_after + 1024, node_cap * 2);
+        CUDA_TRY(ctx, ctx->d_nodes.grow_keep((size_t)ncap * sizeof(PostingNode), (size_t)pairs_inserted * sizeof(PostingNode), ctx->stream));
+        node_cap = ncap;
+        A.table.nodes = ctx->d_nodes.as<PostingNode>();
+    }
+    return NGSID_OK;
+}
+
 int ClusterRun::push_slots()
 {
     if (slots_on_device == n_slots) return NGSID_OK;
@@ -898,9 +926,12 @@ int ClusterRun::insert_slots(int slot0, int count)
     if (rc) return rc;
     rc = ensure_scratch(n_slots);
     if (rc) return rc;
+    rc = ensure_slot_node_capacity(pairs_inserted + add);
+    if (rc) return rc;
     rc = push_slots();
     if (rc) return rc;
-    k2_insert_kernel<<<(count + 7) / 8, 256, 0, ctx->stream>>>(A.table, ctx->d_cursor.as<int32_t>(), ctx->d_slot_read.as<int32_t>(),
+    k2_insert_kernel<<<(count + 7) / 8, 256, 0, ctx->stream>>>(A.table, ctx->d_cursor.as<int32_t>(), (int32_t)std::min<int64_t>(node_cap, 0x7fffffff),
+                                                               d_err.as<int32_t>(), ctx->d_slot_read.as<int32_t>(),
                                                                slot0, count, ctx->d_mins.as<Minimizer>(),
                                                                ctx->d_moff.as<int64_t>(), ctx->d_nmin.as<uint32_t>());
     KERNEL_CHECK(ctx);
@@ -926,7 +957,8 @@ int ClusterRun::run_map(const int32_t *d_list, int n_list)
         CUDA_TRY(ctx, cudaMemcpyAsync(&hdr[0], ctx->d_reqn.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(&hdr[1], d_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (hdr[1]) return fail(ctx, NGSID_EUNSUPPORTED, "more than 8 tied alignment candidates failed for one read");
+        if (hdr[1] == 2) return fail(ctx, NGSID_ENOMEM, "alignment result pool exhausted (more failed tied candidates than reads in the pass)");
+        if (hdr[1]) return fail(ctx, NGSID_ECUDA, "posting node pool overrun (internal error)");
         int nreq = hdr[0];
         if (nreq == 0) return NGSID_OK;
         const AlignRequest *rq = ctx->d_req.as<AlignRequest>();
@@ -938,6 +970,8 @@ int ClusterRun::run_map(const int32_t *d_list, int n_list)
         st.n_alignments += nreq;
         k2_apply_align_kernel<<<(nreq + 255) / 256, 256, 0, ctx->stream>>>(rq, nreq, ctx->d_k4cnt.as<int32_t>(),
                                                                            ctx->d_off.as<int64_t>(), A.params, A.acache,
+                                                                           ctx->d_aovf_head.as<int32_t>(), ctx->d_aovf.as<AlignCacheOvf>(),
+                                                                           d_err.as<int32_t>() + 4, aovf_cap, A.acache_inline,
                                                                            d_list2.as<int32_t>(), d_err.as<int32_t>());
         KERNEL_CHECK(ctx);
         list = d_list2.as<int32_t>();
@@ -1051,11 +1085,21 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     CUDA_TRY(ctx, ctx->d_reqn.ensure(64));
     CUDA_TRY(ctx, ctx->d_k4cnt.ensure((size_t)n * 4 + 64));
     CUDA_TRY(ctx, ctx->d_acache.ensure((size_t)n * ACACHE_N * sizeof(AlignCacheEntry) + 64));
-    CUDA_TRY(ctx, ctx->d_nodes.ensure((size_t)(max_pairs + 1) * sizeof(PostingNode)));
+    R.aovf_cap = std::max(4096, n);
+    CUDA_TRY(ctx, ctx->d_aovf.ensure((size_t)R.aovf_cap * sizeof(AlignCacheOvf)));
+    CUDA_TRY(ctx, ctx->d_aovf_head.ensure((size_t)n * 4 + 64));
+    // Representatives are a small fraction of the reads on amplicon data; the slot arrays and the
+    // posting nodes start at an eighth of the upper bound without surprises and grow on demand
+    // (NGSID_TEST_SMALL_CAPS: tests start them tiny so that every run exercises the growth path).
+    const bool small_caps = getenv("NGSID_TEST_SMALL_CAPS") != nullptr;
+    R.slot_cap = small_caps ? (int)n_init + 4 : (int)n_init + std::max(1024, max_slots / 8);
+    R.node_cap = small_caps ? 64 : std::max<int64_t>(1 << 16, max_pairs / 8);
+    for (int64_t i = 0; i < n_init; ++i) R.node_cap += ctx->h_nmin[init_reps[i]];
+    CUDA_TRY(ctx, ctx->d_nodes.ensure((size_t)R.node_cap * sizeof(PostingNode)));
     CUDA_TRY(ctx, ctx->d_cursor.ensure(64));
-    CUDA_TRY(ctx, ctx->d_slot_read.ensure((size_t)max_slots * 4));
-    CUDA_TRY(ctx, ctx->d_slot_pos.ensure((size_t)max_slots * 4));
-    CUDA_TRY(ctx, ctx->d_slot_state.ensure((size_t)max_slots));
+    CUDA_TRY(ctx, ctx->d_slot_read.ensure((size_t)R.slot_cap * 4));
+    CUDA_TRY(ctx, ctx->d_slot_pos.ensure((size_t)R.slot_cap * 4));
+    CUDA_TRY(ctx, ctx->d_slot_state.ensure((size_t)R.slot_cap));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_params.p, &hp, sizeof(hp), cudaMemcpyHostToDevice, ctx->stream));
     if (n) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_order.p, order, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_accrank.p, acc_rank, (size_t)ctx->n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1063,7 +1107,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     CUDA_TRY(ctx, cudaMemsetAsync(R.d_err.p, 0, 64, ctx->stream));
     if (n) {
         int64_t ne = (int64_t)n * ACACHE_N;
-        k2_fill_acache_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_acache.as<AlignCacheEntry>(), ne);
+        k2_fill_acache_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_acache.as<AlignCacheEntry>(), ctx->d_aovf_head.as<int32_t>(), ne);
         KERNEL_CHECK(ctx);
     }
 
@@ -1083,13 +1127,17 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     A.erru = ctx->d_erru.as<double>();
     A.acc_rank = ctx->d_accrank.as<uint32_t>();
     A.acache = ctx->d_acache.as<AlignCacheEntry>();
+    A.aovf_head = ctx->d_aovf_head.as<int32_t>();
+    A.aovf = ctx->d_aovf.as<AlignCacheOvf>();
+    A.acache_inline = ACACHE_N;
+    if (const char *e = getenv("NGSID_TEST_ACACHE_INLINE")) A.acache_inline = std::max(1, std::min(ACACHE_N, atoi(e)));
     A.dec = ctx->d_dec.as<int32_t>();
     A.via = ctx->d_via.as<uint8_t>();
     A.req = ctx->d_req.as<AlignRequest>();
     A.req_n = ctx->d_reqn.as<int32_t>();
     A.err_flag = R.d_err.as<int32_t>();
 
-    R.slot_read.reserve(max_slots); R.slot_pos.reserve(max_slots); R.slot_state.reserve(max_slots);
+    R.slot_read.reserve(R.slot_cap); R.slot_pos.reserve(R.slot_cap); R.slot_state.reserve(R.slot_cap);
     R.h_dec.assign(n, DEC_NEW);
 
     auto cleanup = [&](int code) {
@@ -1215,7 +1263,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
         if (hi > surprise + 1) {
             int64_t ne = (int64_t)(hi - surprise - 1) * ACACHE_N;
             k2_fill_acache_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(
-                ctx->d_acache.as<AlignCacheEntry>() + (size_t)(surprise + 1) * ACACHE_N, ne);
+                ctx->d_acache.as<AlignCacheEntry>() + (size_t)(surprise + 1) * ACACHE_N, ctx->d_aovf_head.as<int32_t>() + surprise + 1, ne);
             KERNEL_CHECK(ctx);
         }
         pos = surprise + 1;

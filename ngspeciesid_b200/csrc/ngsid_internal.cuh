@@ -24,6 +24,24 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
+    // grows to at least `bytes` and keeps the first `keep` bytes (copied on `stream`; the old block is
+    // freed after the copy has finished)
+    cudaError_t grow_keep(size_t bytes, size_t keep, cudaStream_t stream) {
+        if (bytes <= cap) return cudaSuccess;
+        void *np = nullptr;
+        size_t want = bytes + bytes / 2 + 256;
+        cudaError_t e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&np, bytes); want = bytes; }
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(np, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { cudaFree(np); return e; }
+        }
+        if (p) cudaFree(p);
+        p = np; cap = want;
+        return cudaSuccess;
+    }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
@@ -75,6 +93,7 @@ struct ngsid_ctx {
     DevBuf d_order, d_accrank, d_dec, d_aux, d_via, d_list, d_scratch, d_params;
     DevBuf d_poa_dir, d_poa_arena, d_poa_meta, d_poa_h, d_poa_out, d_poa_len, d_poa_nodes, d_poa_err, d_job_off, d_lsrc, d_lbeg, d_llen;
     DevBuf d_trace, d_ends, d_auxseq, d_aoff, d_win, d_match, d_cols;
+    DevBuf d_aovf, d_aovf_head;
     DevBuf d_req, d_reqn, d_acache, d_k4cnt, d_k4score, d_newslots, d_pa, d_pb, d_po, d_pm;
 };
 

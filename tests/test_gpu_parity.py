@@ -547,3 +547,56 @@ def test_sort_stage_filters_and_file(eng, tmp_path):
     exp = oc.sort_stage(recs, 13)
     assert open(out).read() == "".join("@{0}\n{1}\n+\n{2}\n".format(a, s, q) for a, s, q, _ in exp)
     assert open(tmp_path / "logfile.txt").read().startswith("Lowest read error rate:")
+
+
+def _cluster_vs_oracle(eng, p_table, recs, tile=0, presorted=False):
+    from ngspeciesid_b200 import engine as E
+    ra = oc.read_array_from_sorted(oc.sort_stage(recs, 13)) if not presorted else recs
+    p_emp = oc.load_p_emp(p_table, 13, 20)
+    stats = oc.Stats()
+    oc.single_clustering(ra, p_emp, oc.default_args(), stats)
+    exp = [(-1 if w < 0 else w) for _rid, w, _how in stats.trace]
+    eng.upload_records([(r[3], r[4]) for r in ra])
+    eng.minimizers(13, 20)
+    eng.quality_stats()
+    assign, via, st = eng.cluster(13, 20, E.max_gap_table(p_emp, 0.1), np.arange(len(ra)),
+                                  E.accession_ranks([r[2] for r in ra]), tile_reads=tile)
+    assert list(assign) == exp
+    how = {"new": 0, "map": 1, "align": 2}
+    assert list(via) == [how[h] for _r, _w, h in stats.trace]
+    return st, stats
+
+
+@pytest.mark.parametrize("inline", [1, 2, 8])
+def test_alignment_result_chain_beyond_inline_cache(eng, p_table, inline, monkeypatch):
+    """the reference tries every candidate tied for the top hit count
+    (modules/cluster.py:174-205), so the number of failed candidates a read remembers over the
+    rounds of a pass is unbounded. Templates that share a 288-base prefix tie on its minimizers and
+    fail every alignment; with the inline part of the per-read cache cut to 1 or 2 entries
+    (NGSID_TEST_ACACHE_INLINE) their chains of failed candidates run through the overflow pool."""
+    monkeypatch.setenv("NGSID_TEST_ACACHE_INLINE", str(inline))
+    rng = np.random.default_rng(77)
+    prefix = "".join(rng.choice(list("ACGT"), size=260)) + "AC" * 14
+    recs = []
+    for t in range(14):
+        tmpl = prefix + "T" + "".join(rng.choice(list("ACGT"), size=540))
+        for c in range(3):
+            s = list(tmpl)
+            for _ in range(4):                      # a few substitutions outside the prefix
+                p = int(rng.integers(320, len(s)))
+                s[p] = "ACGT"[("ACGT".index(s[p]) + 1) % 4]
+            recs.append(("t%d_c%d" % (t, c), "".join(s), "I" * len(s)))
+    st, stats = _cluster_vs_oracle(eng, p_table, recs, tile=0)
+    assert st["n_new_reps"] == 14
+    assert stats.alignments >= 20 and stats.aln_passed == 0     # chains of 2-3 failed candidates
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_slot_and_node_pools_grow(eng, p_table, seed, monkeypatch):
+    """slots of invalidated tentative representatives are not reused, so slot
+    arrays and posting nodes are not bounded by the number of reads. The pools start tiny here
+    (NGSID_TEST_SMALL_CAPS) so that the growth path runs many times; result = oracle."""
+    monkeypatch.setenv("NGSID_TEST_SMALL_CAPS", "1")
+    recs = _mixed_reads(600, seed)
+    st, _ = _cluster_vs_oracle(eng, p_table, recs, tile=32)
+    assert st["n_new_reps"] > 60
