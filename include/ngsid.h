@@ -215,6 +215,48 @@ int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t 
                         int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
                         int32_t *out_nodes);
 
+/* ---- multi-GPU data plane (one process per GPU, NCCL over NVLink / NVSwitch) --------------------
+ * Replaces: the exchange of the reference's --t N mode -- modules/parallelize.py:153-187, where the
+ * process pool returns (clusters, representatives, minimizer_database) of every batch to the parent
+ * as pickles -- and the per-cluster read files of the consensus step (modules/consensus.py:249-278,
+ * 186-246). NCCL is loaded at run time (libnccl.so.2, or $NGSID_NCCL_LIB); a context without a
+ * communicator behaves as a world of one rank, so the same driver code runs on one GPU.
+ *
+ * ngsid_nccl_unique_id: rank 0 creates the id (returns its size, <= cap; 128 bytes) and hands it
+ * to the other ranks out of band (file, MPI, torch.distributed, ...). ngsid_nccl_init: collective. */
+int ngsid_nccl_unique_id(uint8_t *out, int64_t cap);
+int ngsid_nccl_init(ngsid_ctx *ctx, const uint8_t *unique_id, int rank, int nranks);
+int ngsid_nccl_finalize(ngsid_ctx *ctx);
+/* A further context on the same GPU borrows the communicator of `owner` (which must outlive it). */
+int ngsid_nccl_share(ngsid_ctx *ctx, ngsid_ctx *owner);
+/* Variable-size all-gather of host bytes (accessions, consensus strings): recv = rank 0's bytes |
+ * rank 1's | ...; counts[r] = bytes of rank r (nranks entries). With recv == NULL only the counts
+ * are exchanged (every rank must then make the same second call with a buffer).                   */
+int ngsid_allgather_bytes(ngsid_ctx *ctx, const uint8_t *send, int64_t n_send, uint8_t *recv,
+                          int64_t recv_cap, int64_t *counts);
+/* In-place all-reduce of a host array of int32 / int64 (elem_bytes 4 / 8); op 0 = sum, 1 = max.  */
+int ngsid_allreduce(ngsid_ctx *ctx, void *buf, int64_t n, int elem_bytes, int op);
+/* Collective. Every rank names its surviving representatives (read indices of ctx, processing
+ * order). Afterwards dst (another context on the same GPU) holds the representatives of ALL ranks,
+ * rank 0's first, as an uploaded read set together with their K1 results (minimizer records,
+ * counts, compressed lengths) and K0 results (error rates, buckets), moved device to device:
+ * ngsid_cluster(dst, ...) runs the merge rounds of modules/parallelize.py:196-215 on them without
+ * recomputing anything. counts[r] = representatives that came from rank r.                       */
+int ngsid_gather_representatives(ngsid_ctx *ctx, const int32_t *reps, int64_t n_reps, ngsid_ctx *dst,
+                                 int64_t *counts);
+/* Collective all-to-all of reads (bases + qualities): read read_idx[i] of ctx goes to rank dest[i]
+ * with the caller's 64-bit tag[i]; entries grouped by ascending dest. Afterwards dst holds the
+ * reads this rank received as an uploaded read set (rank 0's sends first, in the order listed),
+ * out_tag their tags (capacity tag_cap), recv_counts[r] the number that came from rank r.         */
+int ngsid_exchange_reads(ngsid_ctx *ctx, const int32_t *read_idx, const int32_t *dest, const int64_t *tag,
+                         int64_t n_send, ngsid_ctx *dst, int64_t *out_tag, int64_t tag_cap, int64_t *recv_counts);
+/* Doubles the read set: read n + i = reverse complement of read i, qualities reversed (the
+ * polishing step aligns the reads of a reverse-complement-merged centre in both orientations,
+ * modules/consensus.py:148-183).                                                                 */
+int ngsid_append_revcomp(ngsid_ctx *ctx);
+/* Host copy of reads [begin, end) of a context (offsets: end-begin+1 entries, first = 0).         */
+int ngsid_download_reads(ngsid_ctx *ctx, int64_t begin, int64_t end, uint8_t *seq, uint8_t *qual, int64_t *offsets);
+
 #ifdef __cplusplus
 }
 #endif

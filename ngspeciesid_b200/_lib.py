@@ -12,7 +12,9 @@ EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last
            "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
            "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus",
-           "ngsid_fastq_parse"]
+           "ngsid_fastq_parse", "ngsid_nccl_unique_id", "ngsid_nccl_init", "ngsid_nccl_finalize", "ngsid_nccl_share", "ngsid_allgather_bytes",
+           "ngsid_allreduce", "ngsid_gather_representatives", "ngsid_exchange_reads", "ngsid_append_revcomp",
+           "ngsid_download_reads"]
 
 
 class ClusterParams(ctypes.Structure):
@@ -79,6 +81,16 @@ def load():
     lib.ngsid_sg_align_paths.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp]
     lib.ngsid_poa_consensus.argtypes = [vp, P(PoaParams), i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
     lib.ngsid_fastq_parse.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, P(i64)]
+    lib.ngsid_nccl_unique_id.argtypes = [vp, i64]
+    lib.ngsid_nccl_init.argtypes = [vp, vp, i32, i32]
+    lib.ngsid_nccl_finalize.argtypes = [vp]
+    lib.ngsid_nccl_share.argtypes = [vp, vp]
+    lib.ngsid_allgather_bytes.argtypes = [vp, vp, i64, vp, i64, vp]
+    lib.ngsid_allreduce.argtypes = [vp, vp, i64, i32, i32]
+    lib.ngsid_gather_representatives.argtypes = [vp, vp, i64, vp, vp]
+    lib.ngsid_exchange_reads.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, vp]
+    lib.ngsid_append_revcomp.argtypes = [vp]
+    lib.ngsid_download_reads.argtypes = [vp, i64, i64, vp, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)
     _lib = lib

@@ -83,18 +83,21 @@ extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
     return fail(ctx, NGSID_EINVAL, "unknown option");
 }
 
+extern "C" int ngsid_nccl_finalize(ngsid_ctx *ctx);
+
 extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    ngsid_nccl_finalize(ctx);
     DevBuf *bufs[] = {&ctx->d_seq, &ctx->d_qual, &ctx->d_off, &ctx->d_packed, &ctx->d_woff, &ctx->d_flag,
                       &ctx->d_moff, &ctx->d_mins, &ctx->d_nmin, &ctx->d_lenc, &ctx->d_errc, &ctx->d_erru,
                       &ctx->d_bucket, &ctx->d_phred, &ctx->d_thr, &ctx->d_keys, &ctx->d_heads, &ctx->d_nodes,
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
                       &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
-                      &ctx->d_newslots, &ctx->d_aovf, &ctx->d_aovf_head, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+                      &ctx->d_newslots, &ctx->d_cc_a, &ctx->d_cc_b, &ctx->d_cc_c, &ctx->d_aovf, &ctx->d_aovf_head, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
     cudaEventDestroy(ctx->ev0);
@@ -114,12 +117,12 @@ extern "C" int ngsid_sync(ngsid_ctx *ctx)
 }
 
 // ================================================================================ upload + pack
-extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
-                                  const int64_t *offsets, int64_t n_reads)
+// Layout of a new read set: host offsets, word offsets of the packed reads, device buffers sized,
+// d_off / d_woff uploaded. The caller then fills d_seq / d_qual (host or peer data) and calls
+// reads_finish().
+static int reads_layout(ngsid_ctx *ctx, const int64_t *offsets, int64_t n_reads)
 {
-    if (!ctx || !offsets || n_reads < 0 || (n_reads > 0 && (!seq || !qual))) return NGSID_EINVAL;
     if (n_reads >= (int64_t)1 << 31) return fail(ctx, NGSID_EINVAL, "more than 2^31-1 reads");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     ctx->have_min = ctx->have_q = false;
     ctx->h_nmin_valid = false;
     ctx->n_reads = n_reads;
@@ -147,12 +150,18 @@ extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint
     CUDA_TRY(ctx, ctx->d_woff.ensure((n_reads + 1) * sizeof(int64_t)));
     CUDA_TRY(ctx, ctx->d_packed.ensure((size_t)wsum * 4 + 64));
     CUDA_TRY(ctx, ctx->d_flag.ensure(64));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, seq, nb, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qual.p, qual, nb, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_off.p, offsets, (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_off.p, ctx->h_off.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_woff.p, ctx->h_woff.data(), (n_reads + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    return NGSID_OK;
+}
+
+// 2-bit packing of the bases now in d_seq; rejects the read set when a base is outside ACGT.
+static int reads_finish(ngsid_ctx *ctx)
+{
+    const int64_t n_reads = ctx->n_reads;
+    if (n_reads == 0) return NGSID_OK;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, 64, ctx->stream));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_packed.p, 0, (size_t)wsum * 4 + 64, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_packed.p, 0, (size_t)ctx->total_words * 4 + 64, ctx->stream));
     int blocks = (int)std::min<int64_t>((n_reads + 7) / 8, (int64_t)ctx->sm_count * 16);
     cudaEventRecord(ctx->pev[0][0], ctx->stream);
     k_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_off.as<int64_t>(),
@@ -169,6 +178,19 @@ extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint
         return fail(ctx, NGSID_EUNSUPPORTED, "a read contains a base outside ACGT (unsupported in this build)");
     }
     return NGSID_OK;
+}
+
+extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
+                                  const int64_t *offsets, int64_t n_reads)
+{
+    if (!ctx || !offsets || n_reads < 0 || (n_reads > 0 && (!seq || !qual))) return NGSID_EINVAL;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = reads_layout(ctx, offsets, n_reads);
+    if (rc || n_reads == 0) return rc;
+    const size_t nb = (size_t)ctx->total_bases;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, seq, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qual.p, qual, nb, cudaMemcpyHostToDevice, ctx->stream));
+    return reads_finish(ctx);
 }
 
 // ================================================================================ ingest (host)
@@ -1295,3 +1317,5 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     if (stats) *stats = R.st;
     return cleanup(NGSID_OK);
 }
+
+#include "nccl_plane.cuh"

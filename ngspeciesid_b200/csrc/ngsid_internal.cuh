@@ -94,6 +94,12 @@ struct ngsid_ctx {
     DevBuf d_poa_dir, d_poa_arena, d_poa_meta, d_poa_h, d_poa_out, d_poa_len, d_poa_nodes, d_poa_err, d_job_off, d_lsrc, d_lbeg, d_llen;
     DevBuf d_trace, d_ends, d_auxseq, d_aoff, d_win, d_match, d_cols;
     DevBuf d_aovf, d_aovf_head;
+
+    // ---- multi-GPU data plane (nccl_plane.cuh)
+    void *nccl_comm = nullptr;
+    bool nccl_owned = false;
+    int nccl_rank = 0, nccl_nranks = 1;
+    DevBuf d_cc_a, d_cc_b, d_cc_c;
     DevBuf d_req, d_reqn, d_acache, d_k4cnt, d_k4score, d_newslots, d_pa, d_pb, d_po, d_pm;
 };
 

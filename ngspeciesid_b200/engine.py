@@ -85,6 +85,7 @@ class Engine(object):
         self.n_reads = 0
         self.offsets = None
         self._q_done = False
+        self.rank, self.world = 0, 1
         self.poa_shape = 0          # K5 kernel shape used when a call does not say (0 wavefront, 1 row)
         self.poa_order_mode = 0     # row kernel only: 0 spoa's re-sort, 1 path insertion
 
@@ -257,6 +258,84 @@ class Engine(object):
                                                  ptr(aux_seq), ptr(aux_off), n_aux, ptr(out), stride, ptr(out_len), ptr(nodes)))
         return [out[j, :out_len[j]].tobytes().decode("ascii") for j in range(n_jobs)], nodes
 
+    # ---- multi-GPU data plane (NCCL inside the library; a world of one rank without a communicator)
+    def nccl_init(self, unique_id, rank, nranks):
+        uid = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        self._check(self.lib.ngsid_nccl_init(self.h, ptr(uid), rank, nranks))
+        self.rank, self.world = rank, nranks
+
+    def nccl_share(self, owner):
+        """Use the communicator of `owner` (an Engine on the same GPU that called nccl_init)."""
+        self._check(self.lib.ngsid_nccl_share(self.h, owner.h))
+        self.rank, self.world = owner.rank, owner.world
+
+    def allgather_bytes(self, data):
+        """-> list of bytes objects, one per rank."""
+        world = self.world
+        send = np.frombuffer(bytes(data), dtype=np.uint8)
+        counts = np.zeros(world, dtype=np.int64)
+        self._check(self.lib.ngsid_allgather_bytes(self.h, ptr(send), len(send), None, 0, ptr(counts)))     # sizes
+        cap = max(1, int(counts.sum()))
+        recv = np.zeros(cap, dtype=np.uint8)
+        self._check(self.lib.ngsid_allgather_bytes(self.h, ptr(send), len(send), ptr(recv), cap, ptr(counts)))
+        out, o = [], 0
+        for c in counts:
+            out.append(recv[o:o + c].tobytes())
+            o += int(c)
+        return out
+
+    def allreduce(self, arr, op="sum"):
+        """In-place all-reduce of an int32 / int64 numpy array."""
+        assert arr.dtype in (np.int32, np.int64) and arr.flags["C_CONTIGUOUS"]
+        self._check(self.lib.ngsid_allreduce(self.h, ptr(arr), arr.size, arr.dtype.itemsize, 0 if op == "sum" else 1))
+        return arr
+
+    def gather_representatives(self, reps, dst):
+        """Collective: representatives (local read indices) of every rank -> `dst` engine (same GPU),
+        with their minimizers and quality statistics. Returns counts per rank."""
+        reps = as_array(reps, np.int32)
+        counts = np.zeros(self.world, dtype=np.int64)
+        self._check(self.lib.ngsid_gather_representatives(self.h, ptr(reps), len(reps), dst.h, ptr(counts)))
+        dst.n_reads = int(counts.sum())
+        dst.offsets, dst.h_seq, dst.h_qual = None, None, None
+        dst._q_done = True
+        return counts
+
+    def exchange_reads(self, read_idx, dest, tags, dst, expect):
+        """Collective all-to-all of reads into `dst` (same GPU); `expect` = reads this rank will
+        receive (upper bound). Returns (tags of the received reads, counts per source rank)."""
+        read_idx, dest, tags = as_array(read_idx, np.int32), as_array(dest, np.int32), as_array(tags, np.int64)
+        out = np.zeros(max(1, int(expect)), dtype=np.int64)
+        counts = np.zeros(self.world, dtype=np.int64)
+        self._check(self.lib.ngsid_exchange_reads(self.h, ptr(read_idx), ptr(dest), ptr(tags), len(read_idx), dst.h,
+                                                  ptr(out), len(out), ptr(counts)))
+        n = int(counts.sum())
+        dst.n_reads = n
+        dst.offsets, dst.h_seq, dst.h_qual = None, None, None
+        dst._q_done = False
+        return out[:n], counts
+
+    def download_reads(self, begin=0, end=None):
+        """(seq u8, qual u8, offsets i64) of reads [begin, end) as they are on the device."""
+        end = self.n_reads if end is None else end
+        off = np.zeros(end - begin + 1, dtype=np.int64)
+        self._check(self.lib.ngsid_download_reads(self.h, begin, end, None, None, ptr(off)))
+        seq, qual = np.zeros(int(off[-1]), dtype=np.uint8), np.zeros(int(off[-1]), dtype=np.uint8)
+        self._check(self.lib.ngsid_download_reads(self.h, begin, end, ptr(seq), ptr(qual), ptr(off)))
+        return seq, qual, off
+
+    def adopt_device_reads(self):
+        """Host mirror (offsets, bases, qualities) for a read set that arrived through the data plane."""
+        self.h_seq, self.h_qual, self.offsets = self.download_reads()
+        self._qcs = None
+
+    def append_revcomp(self):
+        self._check(self.lib.ngsid_append_revcomp(self.h))
+        n = self.n_reads
+        self.n_reads = 2 * n
+        if self.offsets is not None:
+            self.adopt_device_reads()
+
     def set_option(self, option, value):
         self._check(self.lib.ngsid_set_option(self.h, option, value))
 
@@ -271,6 +350,15 @@ class Engine(object):
 
     def sync(self):
         self._check(self.lib.ngsid_sync(self.h))
+
+
+def nccl_unique_id():
+    """128-byte NCCL id created by the calling rank (hand it to the other ranks out of band)."""
+    buf = np.zeros(128, dtype=np.uint8)
+    n = _lib.load().ngsid_nccl_unique_id(ptr(buf), 128)
+    if n <= 0:
+        raise NgsidError(n, "NCCL is not available (libnccl.so.2 not found; set NGSID_NCCL_LIB)")
+    return buf[:n].tobytes()
 
 
 _ENGINES = {}

@@ -11,6 +11,7 @@ against real parasail). Put this directory first on sys.path to drive the unmodi
 """
 import ctypes
 import os
+import time
 
 _here = os.path.dirname(os.path.abspath(__file__))
 _lib = ctypes.CDLL(os.path.join(_here, "..", "_build", "liboracle.so"))
@@ -20,7 +21,7 @@ _lib.oracle_sg_align.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p,
                                  ctypes.c_char_p, ctypes.POINTER(ctypes.c_int),
                                  ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 
-CALLS = {"n": 0, "cells": 0}
+CALLS = {"n": 0, "cells": 0, "seconds": 0.0}
 
 
 class Matrix(object):
@@ -55,6 +56,7 @@ class _Result(object):
 
 
 def _align(s1, s2, open_, ext, matrix):
+    t0 = time.perf_counter()
     b1, b2 = s1.encode(), s2.encode()
     buf = ctypes.create_string_buffer(len(b1) + len(b2) + 2)
     score, ei, ej = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
@@ -64,6 +66,7 @@ def _align(s1, s2, open_, ext, matrix):
         raise MemoryError("oracle_sg_align")
     CALLS["n"] += 1
     CALLS["cells"] += len(b1) * len(b2)
+    CALLS["seconds"] += time.perf_counter() - t0
     return _Result(score.value, buf.raw[:n], ei.value, ej.value)
 
 
