@@ -1,22 +1,30 @@
 #!/usr/bin/env python
 """
-bench.py -- reads/s clustered on synthetic 750 bp ONT amplicon reads (BASELINE.json config 1:
-100k reads, k=13, w=20, cluster-only) on N B200s.
+bench.py -- reads/s clustered + consensus bp/s on synthetic 750 bp ONT amplicon reads on N B200s
+(BASELINE.json `metric`).
 
-    python bench.py --gpus 1 --steps 3 --warmup 3
+    python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores
+    python bench.py --impl reference ...       # the unmodified reference on the host cores
 
-One "step" = one pass of the clustering hot path (K1 minimizers + K0 quality statistics + the
-greedy pass with K2/K3 mapping and K4 block alignment) over the whole batch.
-  value  : reads/s with the reads already resident in HBM (ASCII + packed), device-timed
-  e2e    : the same through the host-buffer API (pinned host arrays -> H2D -> kernels -> D2H)
-  roofline: K1 (minimizer extraction) timed alone with CUDA events on a replicated input that is
-           far larger than L2, algorithmic bytes = packed read + (offset,len) + 8 B/minimizer + count
-N > 1 follows the reference's --t N semantics (modules/parallelize.py): the score-sorted reads are
-split into N consecutive batches, one per GPU, clustered independently, then log2(N) merge rounds
-exchange representatives (ids only; every rank holds the synthetic pool). Weak scaling: the pool
-has N x reads_per_gpu reads.
+Workloads (config.workload names the one that ran):
+  N = 1, 2, 4 : BASELINE.json configs[1] per GPU: 100 k reads, 10 species, k=13 w=20 (weak scaling:
+                N x 100 k reads, `--t N` semantics of modules/parallelize.py);
+                the consensus leg is configs[2] (cluster + POA consensus + 3 racon-style rounds).
+  N = 8       : BASELINE.json configs[3]: 10^6 reads, 50 species, cluster + consensus with
+                --abundance_ratio 0.005, NCCL exchange of representatives and of cluster reads.
+  --config c1 / c3 forces one of them at any N (reads per GPU: 100 k / 125 k).
+
+One "step" = one pass of the clustering hot path over the whole batch of every rank: K1 minimizers
++ K0 quality statistics + the greedy pass (K2/K3 mapping, K4 block alignment) and, for N > 1, the
+NCCL gather of the surviving representatives + the log2(N) merge rounds.
+  value   : reads/s with the reads resident in HBM, wall clock between device syncs, max over ranks
+  e2e     : the same from pinned host buffers (H2D of bases + qualities inside the timed region,
+            D2H of the assignments)
+  consensus: consensus bp/s of draft + reverse-complement merge + polishing of the FINAL clusters
+  roofline: K1 (minimizer extraction) timed alone with CUDA events on a replicated input far larger
+            than L2; algorithmic bytes = packed read + (offset, len) + 8 B / minimizer + count
+  cpu_baseline: the unmodified reference (baseline/_ref) on a bounded sample, all host cores
 """
 import argparse
 import json
@@ -32,6 +40,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 K, W = 13, 20
+CONFIGS = {
+    "c1": {"reads_per_gpu": 100000, "species": 10, "abundance_ratio": 0.02, "max_seqs": 200, "racon_iter": 3,
+           "name": "BASELINE.json configs[1] (cluster-only; consensus leg = configs[2])"},
+    "c3": {"reads_per_gpu": 125000, "species": 50, "abundance_ratio": 0.005, "max_seqs": 200, "racon_iter": 3,
+           "name": "BASELINE.json configs[3] (cluster + consensus)"},
+}
 
 
 # ------------------------------------------------------------------------------------ workload
@@ -43,7 +57,6 @@ def _vector_scores_block(qual, offsets, k):
     win = cs[k:] - cs[:-k]                     # window starting at flat position i
     lens = np.diff(offsets)
     valid = np.zeros(len(qual), dtype=bool)
-    # windows that stay inside one read
     idx = np.arange(len(qual))
     read_of = np.repeat(np.arange(n), lens)
     valid[: len(win)] = (idx[: len(win)] + k) <= offsets[read_of[: len(win)] + 1]
@@ -56,9 +69,8 @@ def _vector_scores_block(qual, offsets, k):
 
 def vector_scores(qual, offsets, k, block=20000):
     """Expected number of error-free k-mers per read (the reference's sort key,
-    get_sorted_fastq_for_cluster.py:23-33,150-152), vectorised with log-sums; used only to put the
-    synthetic reads in the order the reference's sort stage would. Blocks of reads keep the float64
-    temporaries small (a 900 k-read pool would otherwise need ~40 GB per process)."""
+    get_sorted_fastq_for_cluster.py:23-33,150-152), vectorised with log-sums; only used to put the
+    synthetic reads into the order the reference's sort stage would."""
     n = len(offsets) - 1
     out = np.zeros(n)
     for a in range(0, n, block):
@@ -67,16 +79,17 @@ def vector_scores(qual, offsets, k, block=20000):
     return out
 
 
-def make_workload(n_reads, seed, cache=True):
+def make_workload(n_reads, seed, cache=True, n_species=10, with_templates=False):
     """n_reads synthetic ONT reads that pass the reference's quality filter, in score order.
-    Returns (seq u8, qual u8, offsets i64, accessions list[str])."""
-    path = "/tmp/ngsid_bench_%d_%d.npz" % (n_reads, seed)
+    Returns (seq u8, qual u8, offsets i64, accessions list[str]) [+ templates list[str]]."""
+    path = "/tmp/ngsid_bench_%d_%d_s%d.npz" % (n_reads, seed, n_species)
     if cache and os.path.exists(path):
         z = np.load(path, allow_pickle=False)
-        return z["seq"], z["qual"], z["offsets"], [a.decode() for a in z["acc"]]
+        out = (z["seq"], z["qual"], z["offsets"], [a.decode() for a in z["acc"]])
+        return out + ([t.decode() for t in z["templates"]],) if with_templates else out
     from ngspeciesid_b200.synth import simulate_reads
     gen = int(n_reads * 1.12) + 64
-    rs = simulate_reads(gen, n_species=10, len_lo=700, len_hi=800, seed=seed)
+    rs = simulate_reads(gen, n_species=n_species, len_lo=700, len_hi=800, seed=seed)
     lens = rs.lengths()
     # quality filter of the sort stage (mean uncapped error probability, Q > 7)
     pu = 10.0 ** (-(rs.qual.astype(np.float64) - 33.0) / 10.0)
@@ -94,11 +107,13 @@ def make_workload(n_reads, seed, cache=True):
     seq, qual = rs.seq[src], rs.qual[src]
     acc = ["read%d species=%d strand=%s_%r" % (i, rs.species[i], "+-"[rs.strand[i]], float(s))
            for i, s in zip(order, score_sorted)]
+    templates = [t.tobytes().decode() for t in rs.templates]
     if cache:
         tmp = "%s.%d.tmp.npz" % (path, os.getpid())          # atomic: other ranks may be polling for it
-        np.savez(tmp, seq=seq, qual=qual, offsets=new_off, acc=np.array([a.encode() for a in acc]))
+        np.savez(tmp, seq=seq, qual=qual, offsets=new_off, acc=np.array([a.encode() for a in acc]),
+                 templates=np.array([t.encode() for t in templates]))
         os.replace(tmp, path)
-    return seq, qual, new_off, acc
+    return (seq, qual, new_off, acc, templates) if with_templates else (seq, qual, new_off, acc)
 
 
 def slice_reads(seq, qual, offsets, lo, hi):
@@ -115,6 +130,41 @@ def read_array(seq, qual, offsets, acc, lo, hi):
     return out
 
 
+def batch_bounds(lens, world):
+    from ngspeciesid_b200.multi_gpu import batch_bounds as bb
+    return bb(lens, world)
+
+
+def merge_rounds(eng, params, acc_rank, batch_results, n_batches):
+    """log2 rounds of pairwise consecutive batch merges on ONE engine that holds every read
+    (modules/parallelize.py:137-217); used by the tests of the `--t N` decomposition.
+    batch_results: {batch index (1-based): sorted representative read ids}.
+    Returns ({rep: winner} merges, final reps)."""
+    merges = {}
+    cur = dict(batch_results)
+    while len(cur) > 1:
+        nxt = {}
+        keys = sorted(cur)
+        for j in range(0, len(keys), 2):
+            lo = cur[keys[j]]
+            nb = j // 2 + 1
+            if j + 1 >= len(keys):
+                nxt[nb] = lo
+                continue
+            hi = cur[keys[j + 1]]                        # processed in score order = id order
+            assign, _via, _st = eng.cluster(K, W, params["max_gap"], np.array(hi, dtype=np.int32), acc_rank,
+                                            init_reps=np.array(lo, dtype=np.int32))
+            keep = list(lo)
+            for rid, a in zip(hi, assign):
+                if a >= 0:
+                    merges[rid] = int(a)
+                else:
+                    keep.append(rid)
+            nxt[nb] = sorted(keep)
+        cur = nxt
+    return merges, cur[min(cur)]
+
+
 # ------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -126,7 +176,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -159,84 +209,28 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sampler": "one nvidia-smi poller, GPU of rank 0, 200 ms"}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def merge_rounds(eng, params, acc_rank, batch_results, n_batches):
-    """log2 rounds of pairwise consecutive batch merges (modules/parallelize.py:137-217), given
-    every batch's surviving representatives. batch_results: {batch index (1-based): sorted list of
-    representative read ids (global = uploaded index)}. Returns ({rep: winner} merges, final reps)."""
-    merges = {}
-    cur = dict(batch_results)
-    while len(cur) > 1:
-        nxt = {}
-        keys = sorted(cur)
-        for j in range(0, len(keys), 2):
-            lo = cur[keys[j]]
-            nb = j // 2 + 1
-            if j + 1 >= len(keys):
-                nxt[nb] = lo
-                continue
-            hi = cur[keys[j + 1]]                        # processed in score order = id order
-            assign, _via, _st = eng.cluster(K, W, params["max_gap"], np.array(hi, dtype=np.int32), acc_rank,
-                                            init_reps=np.array(lo, dtype=np.int32))
-            keep = list(lo)
-            for rid, a in zip(hi, assign):
-                if a >= 0:
-                    merges[rid] = int(a)
-                else:
-                    keep.append(rid)
-            nxt[nb] = sorted(keep)
-        cur = nxt
-    return merges, cur[min(cur)]
-
-
-def batch_bounds(lens, world):
-    """Read index bounds of the `world` consecutive batches of the score-sorted list
-    (modules/parallelize.py:54-67: cut after the read that fills int(total_nt / N) + 1 nucleotides)."""
-    n_total = len(lens)
-    bounds = [0]
-    if world > 1:
-        limit = int(lens.sum() / world) + 1
-        csum = np.cumsum(lens)
-        base = 0
-        while len(bounds) < world:
-            j = int(np.searchsorted(csum, base + limit, side="left"))
-            if j >= n_total:
-                break
-            bounds.append(j + 1)
-            base = int(csum[j])
-    while len(bounds) < world + 1:
-        bounds.append(n_total)
-    return bounds
-
-
-def merge_representatives(eng2, seq, qual, offsets, acc, gathered, params):
-    """gathered[b] = global read ids of the representatives batch b ended with. Uploads these reads
-    only, runs the merge rounds and returns ({merged representative: winner}, final representatives),
-    both in global read ids."""
-    from ngspeciesid_b200 import engine as E
-    ids = sorted(set(x for g in gathered for x in g))
-    if not ids:
-        return {}, []
-    idx = {g: i for i, g in enumerate(ids)}
-    parts = [slice_reads(seq, qual, offsets, g, g + 1) for g in ids]
-    m_seq = np.concatenate([p[0] for p in parts]); m_qual = np.concatenate([p[1] for p in parts])
-    m_off = np.zeros(len(ids) + 1, dtype=np.int64)
-    np.cumsum([len(p[0]) for p in parts], out=m_off[1:])
-    eng2.upload(m_seq, m_qual, m_off)
-    eng2.minimizers(K, W)
-    eng2.quality_stats()
-    ar = E.accession_ranks([acc[g] for g in ids])
-    merges, final = merge_rounds(eng2, params, ar, {b + 1: [idx[x] for x in g] for b, g in enumerate(gathered)}, len(gathered))
-    return {ids[a]: ids[b] for a, b in merges.items()}, [ids[i] for i in final]
+def pick_config(args, world):
+    name = args.config if args.config != "auto" else ("c3" if world >= 8 else "c1")
+    cfg = dict(CONFIGS[name])
+    if args.reads:
+        cfg["reads_per_gpu"] = args.reads
+    for key in ("abundance_ratio", "max_seqs", "racon_iter"):
+        v = getattr(args, key)
+        if v is not None:
+            cfg[key] = v
+    cfg["key"] = name
+    return cfg
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from ngspeciesid_b200 import engine as E
+    from ngspeciesid_b200 import multi_gpu as M
     from ngspeciesid_b200.modules import p_minimizers_shared
 
     rank = int(os.environ.get("RANK", "0"))
@@ -247,29 +241,38 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    n_total = args.reads * world
+    cfg = pick_config(args, world)
+    n_total = cfg["reads_per_gpu"] * world
+    seed = args.seed + world - 1
     if world > 1:
         # rank 0 generates (or finds) the pool and leaves it in the cache; the others load it
         if rank == 0:
-            make_workload(n_total, args.seed + world - 1)
+            make_workload(n_total, seed, n_species=cfg["species"])
         dist.barrier()
-    seq, qual, offsets, acc = make_workload(n_total, args.seed + world - 1)
+    seq, qual, offsets, acc, templates = make_workload(n_total, seed, n_species=cfg["species"], with_templates=True)
     p_emp = p_minimizers_shared.p_emp_for(K, W)
-    params = {"max_gap": E.max_gap_table(p_emp, 0.1)}
+    max_gap = E.max_gap_table(p_emp, 0.1)
 
     # --t N semantics: N consecutive batches of the score-sorted list by cumulative nucleotides
     bounds = batch_bounds(np.diff(offsets), world)
     lo, hi = bounds[rank], bounds[rank + 1]
     n_mine = hi - lo
-
-    eng = E.Engine(local)
     s_seq, s_qual, s_off = slice_reads(seq, qual, offsets, lo, hi)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     h_seq, h_qual, h_off = pin(s_seq), pin(s_qual), pin(s_off)
     my_acc = acc[lo:hi]
-    acc_rank = E.accession_ranks(my_acc)
-    order = np.arange(n_mine, dtype=np.int32)
+    my_scores = [float(a.split("_")[-1]) for a in my_acc]
+    del seq, qual                                     # every rank keeps its own batch only
+
+    eng, mg, ce, pe = E.Engine(local), E.Engine(local), E.Engine(local), E.Engine(local)
+    if world > 1:
+        # the library's own communicator (NCCL inside libngsid.so); the id travels over torch.distributed
+        uid = [E.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.nccl_init(uid[0], rank, world)
+        for e in (mg, ce, pe):
+            e.nccl_share(eng)
+    pipe = M.Pipeline(eng, mg, ce, pe, rank=rank, world=world, k=K, w=W)
 
     def barrier():
         if world > 1:
@@ -280,205 +283,144 @@ def run_ours(args):
     state = {}
 
     def step(e2e):
-        if e2e:
-            eng.upload(h_seq, h_qual, h_off)
-        eng.minimizers(K, W)
-        eng.quality_stats()
-        assign, via, st = eng.cluster(K, W, params["max_gap"], order, acc_rank, tile_reads=args.tile)
-        state["assign"], state["via"], state["stats"] = assign, via, st
-        if world > 1:
-            # exchange surviving representatives (global ids) and run the merge rounds
-            reps = [int(lo + i) for i in np.nonzero(assign == -1)[0]]
-            gathered = [None] * world
-            dist.all_gather_object(gathered, reps)
-            state["gathered"] = gathered
-        return assign
+        up = (h_seq, h_qual, h_off) if e2e else None
+        state["roots"] = pipe.cluster(max_gap, my_acc, my_scores, lo, n_total, upload=up, tile_reads=args.tile)
 
-    def merge_on_rank0():
-        """Merge rounds over the representatives of all batches (few hundred reads at most):
-        run once on rank 0 inside the timed region of every step."""
-        eng2 = state.setdefault("eng2", E.Engine(local))
-        return merge_representatives(eng2, seq, qual, offsets, acc, state["gathered"], params)
+    def engines_launches():
+        return sum(e.launch_count() for e in (eng, mg, ce, pe))
 
-    def full_step(e2e):
-        step(e2e)
-        if world > 1:
-            if rank == 0:
-                state["merge"] = merge_on_rank0()
-            dist.barrier()
-
-    # ---- warm-up + resident timing (device events on the engine's stream, max over ranks)
+    # ---- warm-up + resident timing
     eng.upload(h_seq, h_qual, h_off)
     for _ in range(args.warmup):
-        full_step(False)
-    sampler = ClockSampler(local)
+        step(False)
+    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
-    sampler.start()
-    eng.reset_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+    for e in (eng, mg, ce, pe):
+        e.reset_launch_count()
+    pipe.phase = {}
+    dev = {"k1": 0.0, "k0": 0.0, "cluster": 0.0, "k4": 0.0, "map": 0.0}
     t0 = time.perf_counter()
-    phase = {"k1": 0.0, "k0": 0.0, "cluster": 0.0, "k4": 0.0, "map": 0.0}
     for _ in range(args.steps):
-        full_step(False)
-        phase["k1"] += eng.phase_ms(1); phase["k0"] += eng.phase_ms(2); phase["cluster"] += eng.phase_ms(3)
-        phase["k4"] += eng.phase_ms(4); phase["map"] += eng.phase_ms(5)
+        step(False)
+        dev["k1"] += eng.phase_ms(1); dev["k0"] += eng.phase_ms(2); dev["cluster"] += eng.phase_ms(3)
+        dev["k4"] += eng.phase_ms(4); dev["map"] += eng.phase_ms(5)
     barrier()
     dt = time.perf_counter() - t0
-    launches = eng.launch_count() + (state["eng2"].launch_count() if "eng2" in state else 0)
-    clocks = sampler.stop()
-    # device-event time of the steps (sum of the phases; host orchestration gaps are inside `cluster`)
-    dev_ms = (phase["k1"] + phase["k0"] + phase["cluster"])
-    # ---- end-to-end (host buffers -> H2D -> kernels -> D2H), wall clock bracketed by syncs
-    for _ in range(1):
-        full_step(True)
+    launches = engines_launches()
+    phase_res = dict(pipe.phase)
+    # ---- end to end (pinned host buffers -> H2D -> kernels -> D2H), same loop
+    step(True)
     barrier()
+    pipe.phase = {}
     t1 = time.perf_counter()
     for _ in range(args.steps):
-        full_step(True)
+        step(True)
     barrier()
     dt_e2e = time.perf_counter() - t1
+    clocks = sampler.stop() if sampler else None
+    phase_e2e = dict(pipe.phase)
 
+    def over_ranks(d, steps=None):
+        """{phase: (max, min) over ranks} of per-step milliseconds."""
+        keys = sorted(d)
+        v = torch.tensor([d[k_] * 1000.0 / (steps or args.steps) for k_ in keys], dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx, mn = v.clone(), v.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        else:
+            mx = mn = v
+        return {k_: {"max": float(a), "min": float(b)} for k_, a, b in zip(keys, mx.tolist(), mn.tolist())}
+
+    phases = {"resident": over_ranks(phase_res), "e2e": over_ranks(phase_e2e),
+              "device": over_ranks({k_: v / 1000.0 for k_, v in dev.items()})}
     if world > 1:
-        t = torch.tensor([dt, dt_e2e, dev_ms / 1000.0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, dt_e2e, dev_s = [float(x) for x in t.tolist()]
-        dev_ms = dev_s * 1000.0
+        t = torch.tensor([dt, dt_e2e, float(launches)], dtype=torch.float64, device="cuda")
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dt, dt_e2e = float(mx[0]), float(mx[1])
+        launches = int(sm[2])
 
     result = None
+    st = pipe.local_stats
+    n_final = len(pipe.ms.final_reps())
     if rank == 0:
-        st = state["stats"]
         value = n_total * args.steps / dt
         e2e_v = n_total * args.steps / dt_e2e
         result = {
-            "metric": "reads/sec clustered (750 bp ONT amplicons, k=13 w=20, cluster-only)",
+            "metric": "reads/sec clustered + consensus bp/sec, 750bp ONT amplicons, 1/2/4/8 B200",
             "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1000.0 / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32/int32 (doubles for error rates)", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: %d synthetic 750 bp ONT-error reads per GPU, 10 species, "
-                                   "k=13 w=20, cluster-only, --t %d semantics" % (args.reads, world),
-                       "reads_per_gpu": args.reads, "total_reads": n_total, "timing": "wall clock between stream syncs "
-                       "(host orchestrates the greedy pass); device-event sum reported as device_ms_per_step",
-                       "l2": "inputs_exceed_l2 (ASCII+packed reads + minimizers = %.0f MB per GPU)" %
-                             ((offsets[hi] - offsets[lo]) * 2.25 / 1e6 + n_mine * 119 * 8 / 1e6),
-                       "tile_reads": args.tile or 65536},
-            "device_ms_per_step": dev_ms / args.steps,
-            "phase_ms_per_step": {k_: v / args.steps for k_, v in phase.items()},
+            "vs_baseline": None, "dtype": "u32/int32 (f64 for error rates)", "data": "synthetic",
+            "config": workload_config(cfg, world),
+            "timing": "wall clock between device syncs, max over ranks (the host orchestrates the greedy pass); "
+                      "per-phase milliseconds per step as max/min over ranks in `phases`",
+            "phases": phases,
             "e2e": {"value": e2e_v, "unit": "reads/s",
-                    "h2d_bytes_per_step": int(h_seq.nbytes + h_qual.nbytes + h_off.nbytes + acc_rank.nbytes + order.nbytes) * world,
-                    "d2h_bytes_per_step": int(n_mine * 5) * world},
+                    "h2d_bytes_per_step": int(offsets[-1]) * 2 + 8 * (n_total + world) + 8 * n_total,
+                    "d2h_bytes_per_step": int(n_total * 5)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "cluster_stats": st,
+            "cluster_stats_rank0": st, "final_clusters": n_final, "merge_rounds": pipe.merge_rounds,
         }
-        if st["align_cells"] and phase["k4"] > 0:
-            result["k4_gcups"] = st["align_cells"] * args.steps / (phase["k4"] / 1000.0) / 1e9
+        if st["align_cells"] and dev["k4"] > 0:
+            result["k4_gcups_rank0"] = st["align_cells"] * args.steps / (dev["k4"] / 1000.0) / 1e9
 
-
-    # ---- consensus leg (BASELINE.json configs[2] shape): draft POA + racon-style polish of every
-    # cluster above the abundance cut-off, capped with the reference's own --max_seqs_for_consensus.
-    # N > 1: clusters shard -- every rank polishes the clusters of its own batch (as they stand
-    # before the cross-batch merge rounds); no data-path collective, the aggregate is the sum of the
-    # bases over the slowest rank's time.
+    # ---- consensus of the FINAL clusters (NGSpeciesID:124-158), clusters sharded over the ranks
     if not args.no_consensus:
-        from ngspeciesid_b200.modules import consensus as C
-        assign = state["assign"]
-        rep = np.where(assign >= 0, assign, np.arange(n_mine))
-        cutoff = int(args.abundance_ratio * n_mine)
-        ids, counts = np.unique(rep, return_counts=True)
-        big = ids[counts >= cutoff]
-        order_idx = np.argsort(rep, kind="stable")
-        starts = np.searchsorted(rep[order_idx], big)
-        lists = [order_idx[st:st + c][: args.max_seqs].tolist() for st, c in zip(starts, counts[counts >= cutoff])]
-        lens_ = np.diff(s_off)
-        used_bases = int(sum(int(lens_[l].sum()) for l in lists))
-
-        def consensus_step():
-            drafts, _nodes = C.draft_consensus_batch(eng, lists)
-            return C.polish_batch(eng, drafts, lists, args.racon_iter)
-
-        l0 = eng.launch_count()
-        consensus_step()
+        pipe.phase = {}
+        for e in (eng, mg, ce, pe):
+            e.reset_launch_count()
+        centers, info = pipe.consensus(cfg["abundance_ratio"], cfg["max_seqs"], cfg["racon_iter"])     # warm-up
         barrier()
-        tc = time.perf_counter()
+        pipe.phase = {}
         csteps = max(1, min(args.steps, 2))
+        l0 = engines_launches()
+        tc = time.perf_counter()
         for _ in range(csteps):
-            cons = consensus_step()
+            centers, info = pipe.consensus(cfg["abundance_ratio"], cfg["max_seqs"], cfg["racon_iter"])
         barrier()
-        dtc_ = (time.perf_counter() - tc) / csteps
-        mine = {"bases": used_bases, "seconds": dtc_, "clusters": len(lists), "reads": int(sum(len(l) for l in lists)),
-                "launches": int(eng.launch_count() - l0)}
-        allc = [mine]
+        dtc = (time.perf_counter() - tc) / csteps
+        cl = engines_launches() - l0
+        cph = dict(pipe.phase)
         if world > 1:
-            allc = [None] * world
-            dist.all_gather_object(allc, mine)
+            t = torch.tensor([dtc], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t[0])
+            t = torch.tensor([float(cl)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            cl = int(t[0])
+        cphase = over_ranks(cph, csteps)
+        # read bases consumed: every read of the draft step once, every read of the polishing step per round
+        lens_mean = float(offsets[-1]) / n_total
+        bases = (info["reads_draft"] + info["reads_polish"] * cfg["racon_iter"]) * lens_mean
         if rank == 0:
-            dtc_ = max(x["seconds"] for x in allc)
+            from oracle import consensus_oracle as co     # checker only: distance of the results to the templates
+            rc = lambda s: co.revcomp(s)
+            dists = []
+            for _n, _cid, cons in centers[:12]:
+                best = min(min(co.edit_distance(cons, t_), co.edit_distance(cons, rc(t_))) for t_ in templates)
+                dists.append(best / float(len(cons)))
             result["consensus"] = {
-                "metric": "consensus bp/s (read bases consumed by draft POA + %d polish rounds / wall time)" % args.racon_iter,
-                "value": sum(x["bases"] for x in allc) * (1 + args.racon_iter) / dtc_, "unit": "bp/s", "seconds_per_step": dtc_,
-                "clusters": sum(x["clusters"] for x in allc), "reads_used": sum(x["reads"] for x in allc),
-                "config": "clusters >= abundance_ratio %.3f x reads, --max_seqs_for_consensus %d, --racon_iter %d; host buffers in, "
-                          "consensus strings out%s" % (args.abundance_ratio, args.max_seqs, args.racon_iter,
-                                                       "; clusters of each batch on its own GPU, max over ranks" if world > 1 else ""),
-                "consensus_lengths": [len(c) for c in cons][:8], "gpu_launches": sum(x["launches"] for x in allc)}
-        if rank == 0 and not args.no_cpu and lists:
-            from oracle import consensus_oracle as co
-            sample = lists[0][: args.cpu_consensus_reads]
-            recs = [(s_seq[s_off[i]:s_off[i + 1]].tobytes().decode(), s_qual[s_off[i]:s_off[i + 1]].tobytes().decode()) for i in sample]
-            t3 = time.perf_counter()
-            d0 = co.spoa_consensus(recs)
-            p0 = co.racon_polish(d0, recs, args.racon_iter)
-            dt3 = time.perf_counter() - t3
-            sb = sum(len(r[0]) for r in recs)
-            g_d, _ = C.draft_consensus_batch(eng, [sample])
-            g_p = C.polish_batch(eng, g_d, [sample], args.racon_iter)[0]
-            result["consensus"]["cpu_baseline"] = {
-                "value": sb * (1 + args.racon_iter) / dt3, "unit": "bp/s", "cores": 1, "kind": "port",
-                "sample": "first %d reads of the largest cluster, oracle/poa_oracle.cpp + consensus_oracle.py" % len(sample)}
-            result["consensus"]["parity_sample_edit_distance"] = int(co.edit_distance(g_p, p0))
+                "metric": "consensus bp/s (read bases consumed by the draft POA + %d polishing rounds / wall time), FINAL clusters"
+                          % cfg["racon_iter"],
+                "value": bases / dtc, "unit": "bp/s", "seconds_per_step": dtc,
+                "clusters_selected": info["clusters_selected"], "centres_after_rc_merge": info["centres_after_rc_merge"],
+                "reads_draft": info["reads_draft"], "reads_polish_per_round": info["reads_polish"],
+                "config": "clusters >= abundance_ratio %.3f x reads after the merge rounds, --max_seqs_for_consensus %d, "
+                          "--racon_iter %d, --rc_identity_threshold 0.9; clusters sharded over %d rank(s), reads moved by "
+                          "ngsid_exchange_reads" % (cfg["abundance_ratio"], cfg["max_seqs"], cfg["racon_iter"], world),
+                "phases": cphase, "gpu_launches": cl,
+                "consensus_lengths": [len(c[2]) for c in centers][:12],
+                "edit_distance_to_nearest_template_per_base": [round(d, 5) for d in dists]}
+        # CPU baseline of the consensus leg: the oracle (restated spoa / racon) on whole clusters, one per core
+        if rank == 0 and not args.no_cpu and info["clusters_selected"]:
+            result["consensus"]["cpu_baseline"] = consensus_cpu_baseline(pipe, ce, info, cfg, lens_mean)
 
-    # ---- sort stage in front of the path (SURVEY.md 8 f rank 1): scores on the GPU, stable sort on the host
-    if rank == 0 and not args.no_consensus:
-        eng.sort_scores(K)
-        eng.sync()
-        ts = time.perf_counter()
-        for _ in range(3):
-            sc, er = eng.sort_scores(K)
-            srt_order = np.argsort(-sc, kind="stable")
-        dts = (time.perf_counter() - ts) / 3
-        result["sort_stage"] = {"metric": "reads/s scored + ordered (get_sorted_fastq_for_cluster arithmetic; reads resident, "
-                                          "scores D2H, stable argsort on the host)", "value": n_mine / dts, "unit": "reads/s",
-                                "ms": dts * 1e3, "reads": int(n_mine)}
-        if not args.no_cpu:
-            from oracle import cluster_oracle as oc
-            ns_ = min(n_mine, 2000)
-            t4 = time.perf_counter()
-            ref_sc = [oc.expected_error_free_kmers_score(s_qual[s_off[i]:s_off[i + 1]].tobytes().decode(), K) for i in range(ns_)]
-            dt4 = time.perf_counter() - t4
-            result["sort_stage"]["cpu_baseline"] = {"value": ns_ / dt4, "unit": "reads/s", "cores": 1, "kind": "port",
-                                                    "sample": "first %d reads, oracle/cluster_oracle.py" % ns_}
-            result["sort_stage"]["parity_sample_identical"] = bool(ref_sc == [float(x) for x in sc[:ns_]])
-
-    # ---- ingest in front of the sort stage (SURVEY.md 8 f rank 3): host C parser vs the generator
-    if rank == 0 and not args.no_consensus:
-        import io
-        from ngspeciesid_b200.modules import help_functions as hf
-        ni = min(n_mine, 20000)
-        text = "".join("@%s\n%s\n+\n%s\n" % (my_acc[i], s_seq[s_off[i]:s_off[i + 1]].tobytes().decode(),
-                                               s_qual[s_off[i]:s_off[i + 1]].tobytes().decode()) for i in range(ni))
-        data = text.encode()
-        t5 = time.perf_counter()
-        fa = hf.parse_fastq_bytes(data)
-        dt5 = time.perf_counter() - t5
-        t6 = time.perf_counter()
-        n_py = sum(1 for _ in hf.readfq(io.StringIO(text)))
-        dt6 = time.perf_counter() - t6
-        result["ingest"] = {"metric": "FASTQ bytes/s parsed into upload-ready arrays (ngsid_fastq_parse, host, 1 thread)",
-                            "value": len(data) / dt5, "unit": "B/s", "reads": int(len(fa)), "bytes": len(data),
-                            "cpu_baseline": {"value": len(data) / dt6, "unit": "B/s", "cores": 1, "kind": "port",
-                                             "sample": "the same %d records through the readfq generator mirror" % n_py},
-                            "parity_identical": bool(len(fa) == n_py == ni and (fa.seq == s_seq[:s_off[ni]]).all()
-                                                     and (fa.qual == s_qual[:s_off[ni]]).all())}
+    # ---- the same 100 k reads through the drop-in modules API (tuples in, dicts out)
+    if rank == 0 and world == 1 and not args.no_modules:
+        result["e2e_modules"] = modules_leg(s_seq, s_qual, s_off, my_acc, p_emp, pipe, local)
 
     # ---- K1 roofline on a replicated input far larger than L2 (rank 0 only)
     if rank == 0 and not args.no_roofline:
@@ -499,7 +441,6 @@ def run_ours(args):
         except Exception:
             pass
         achieved = alg_bytes / (ms / 1000.0) / 1e9
-        # DRAM traffic of one launch from the committed ncu --set full capture (same command, same size)
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
@@ -507,109 +448,139 @@ def run_ours(args):
                 traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"]); traffic_src = tj["source"]
         except Exception:
             pass
-        result["roofline"] = {"kernel": "k1_stream_kernel (thread per read: compress + window minima; warp per 32 reads: output)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                              "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                              "algorithmic_bytes_per_launch": int(alg_bytes), "bound_note": "reported against HBM as BASELINE asks; the kernel is ALU-issue bound (DESIGN.md 4.0/4.1)",
+        result["roofline"] = {"kernel": "k1_stream_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                              "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                              "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(alg_bytes),
+                              "bound_note": "reported against HBM as BASELINE asks; the kernel is ALU-issue bound (DESIGN.md 4.0/4.1)",
                               "reads_per_launch": int(len(blens)), "bytes_per_read": alg_bytes / len(blens),
                               "kernel_ms": ms, "reads_per_s": len(blens) / (ms / 1000.0)}
         eng.upload(h_seq, h_qual, h_off)
 
-    # ---- CPU baseline: the oracle port on a bounded prefix of the same ordered workload
-    if rank == 0 and not args.no_cpu:
+    # ---- CPU baseline: the unmodified reference on a bounded prefix of the same ordered workload
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from baseline import reference_arm
+        cores = os.cpu_count() or 1
+        cb = reference_arm.measure(s_seq, s_qual, s_off, my_acc, K, W, 1, 1, 0, cores, budget_s=args.cpu_budget, tag="cpu")
+        result["cpu_baseline"] = {"value": cb["value"], "unit": "reads/s", "cores": cb["cores"], "kind": cb["kind"],
+                                  "sample": cb["sample"], "one_core_reads_per_s": cb["one_copy_reads_per_s"],
+                                  "aligner_seconds_share": cb["aligner_seconds_share"]}
+        # parity on the sample: the oracle (pinned to the reference's golden vectors) on the same prefix
         from oracle import cluster_oracle as oc
-        ns = min(args.cpu_sample, n_mine)
-        ra = read_array(seq, qual, offsets, acc, 0, ns)
+        ns = min(cb["sample_reads"], n_mine, 4000)
+        ra = read_array(s_seq, s_qual, s_off, my_acc, 0, ns)
         stats = oc.Stats()
-        t2 = time.perf_counter()
         oc.single_clustering(ra, p_emp, oc.default_args(), stats)
-        dtc = time.perf_counter() - t2
         exp = [w_ for _r, w_, _h in stats.trace]
-        got = [int(x) for x in state["assign"][:ns]] if world == 1 else None
-        result["cpu_baseline"] = {"value": ns / dtc, "unit": "reads/s", "cores": 1, "kind": "port",
-                                  "sample": "first %d reads of the same score-ordered workload, oracle/cluster_oracle.py "
-                                            "(Python restatement + C aligner), single thread" % ns}
-        if got is not None:
-            result["parity_sample_identical"] = bool(got == exp)
+        result["parity_sample_identical"] = bool([int(x) for x in pipe.local_assign[:ns]] == exp)
     if rank == 0:
         print(json.dumps(result))
     if world > 1:
         dist.barrier()
+        for e in (pe, ce, mg, eng):
+            e.close()
         dist.destroy_process_group()
 
 
+def workload_config(cfg, world):
+    return {"workload": "%s: %d synthetic 750 bp ONT-error reads per GPU (%d in total), %d species, k=13 w=20, --t %d semantics"
+                        % (cfg["name"], cfg["reads_per_gpu"], cfg["reads_per_gpu"] * world, cfg["species"], world),
+            "reads_per_gpu": cfg["reads_per_gpu"], "total_reads": cfg["reads_per_gpu"] * world, "species": cfg["species"],
+            "l2": "inputs_exceed_l2 (ASCII + packed reads + minimizer records = %.0f MB per GPU)"
+                  % (cfg["reads_per_gpu"] * (750 * 2.25 + 119 * 8) / 1e6)}
+
+
+def _consensus_cpu_worker(job):
+    from oracle import consensus_oracle as co
+    recs, iters = job
+    t0 = time.perf_counter()
+    d = co.spoa_consensus(recs)
+    p = co.racon_polish(d, recs, iters, both_strands=False)
+    return time.perf_counter() - t0, len(p)
+
+
+def consensus_cpu_baseline(pipe, ce, info, cfg, lens_mean):
+    """oracle/poa_oracle.cpp + consensus_oracle.py (the restated spoa / racon; -O3, scalar) on WHOLE clusters
+    of the draft step, one cluster per host core at the same time."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    seq, qual, off = ce.h_seq, ce.h_qual, ce.offsets
+    n_have = len(off) - 1
+    per = cfg["max_seqs"] if cfg["max_seqs"] > 0 else 200
+    jobs = []
+    for j in range(min(cores, max(1, n_have // per))):
+        ids = range(j * per, min(n_have, (j + 1) * per))
+        jobs.append(([(seq[off[i]:off[i + 1]].tobytes().decode(), qual[off[i]:off[i + 1]].tobytes().decode()) for i in ids],
+                     cfg["racon_iter"]))
+    if not jobs:
+        return None
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        res = pool.map(_consensus_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    bases = sum(sum(len(r[0]) for r in j[0]) for j in jobs) * (1 + cfg["racon_iter"])
+    return {"value": bases / dt, "unit": "bp/s", "cores": len(jobs), "kind": "port",
+            "sample": "%d whole read sets of %d reads (draft + %d polishing rounds each), one per core, oracle/poa_oracle.cpp "
+                      "-O3 scalar + consensus_oracle.py; spoa / racon themselves are not in this image"
+                      % (len(jobs), per, cfg["racon_iter"]),
+            "seconds": dt, "slowest_job_seconds": max(r[0] for r in res)}
+
+
+def modules_leg(s_seq, s_qual, s_off, my_acc, p_emp, pipe, device):
+    """The call a user of the reference makes: modules.parallelize.single_clustering(read_array, p_emp_probs,
+    args) -- list of tuples in, (clusters, representatives) dicts out -- on the same reads."""
+    from ngspeciesid_b200.modules import parallelize
+    from baseline import reference_arm
+    n = len(my_acc)
+    ra = read_array(s_seq, s_qual, s_off, my_acc, 0, n)
+    a = reference_arm.reference_args(K, W, 1, None)      # the reference's CLI defaults
+    a.device = device
+    parallelize.single_clustering(list(ra), p_emp, a)              # warm-up
+    steps = 3
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        clusters, reps = parallelize.single_clustering(list(ra), p_emp, a)
+    dt = (time.perf_counter() - t0) / steps
+    # same clustering as the array-level path
+    exp = {}
+    for i, r in enumerate(pipe.local_assign):
+        exp.setdefault(int(r) if r >= 0 else i, []).append(my_acc[i])
+    same = {k_: v for k_, v in clusters.items()} == exp
+    return {"metric": "reads/s through modules.parallelize.single_clustering (Python tuples in, dicts out)",
+            "value": n / dt, "unit": "reads/s", "seconds_per_call": dt, "reads": n,
+            "clusters_equal_array_path": bool(same), "clusters": len(clusters)}
+
+
 # ------------------------------------------------------------------------------------ reference arm
-def _ref_worker(job):
-    from oracle import cluster_oracle as oc
-    ra, p_emp, bi = job
-    clusters = {r[0]: [r[2]] for r in ra}
-    reps = {r[0]: tuple(r) for r in ra}
-    res = oc.reads_to_clusters(clusters, reps, ra, p_emp, {}, bi, oc.default_args())
-    return res[bi]
-
-
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    import multiprocessing as mp
-    from oracle import cluster_oracle as oc
-    from ngspeciesid_b200.modules import p_minimizers_shared
+    from baseline import reference_arm
+    world = max(1, world, args.gpus if "WORLD_SIZE" not in os.environ else 1)
+    cfg = pick_config(args, world)
     cores = os.cpu_count() or 1
-    n_total = args.reads * max(1, world)
-    seq, qual, offsets, acc = make_workload(n_total, args.seed + max(1, world) - 1)
-    p_emp = p_minimizers_shared.p_emp_for(K, W)
-    # bounded sample: about two minutes of CPU work for the whole run whatever --steps is
-    # (the port clusters ~300 reads/s per core)
-    per_core = min(args.ref_reads_per_core, max(100, int(120 * 300 / max(1, args.steps))))
-    ns = min(n_total, per_core * cores)
-    ra = read_array(seq, qual, offsets, acc, 0, ns)
-    a = oc.default_args(nr_cores=cores)
-    batches = [b for b in oc.split_batches(ra, cores, "total_nt") if b]
-
-    def one_step():
-        with mp.get_context("fork").Pool(len(batches)) as pool:
-            res = pool.map(_ref_worker, [(b, p_emp, i + 1) for i, b in enumerate(batches)])
-        # merge rounds (tiny) in-process, as the reference does after joining the pool
-        all_cl, all_rp, all_db = {}, {}, {}
-        for c, r, d, bi in res:
-            all_cl.update(c); all_rp.update(r); all_db[bi] = d
-        arr = [(v[0], v[1], v[2], v[3], v[4], v[5]) for _, v in sorted(all_rp.items(), key=lambda x: x[1][5], reverse=True)]
-        while True:
-            groups = oc.pair_batches(arr)
-            if len(groups) <= 1 and len(all_db) <= 1:
-                break
-            n_all_cl, n_all_rp, n_all_db = {}, {}, {}
-            for gi, g in enumerate(groups):
-                low = min(r[1] for r in g)
-                cl = {r[0]: all_cl[r[0]] for r in g}; rp = {r[0]: all_rp[r[0]] for r in g}
-                out = oc.reads_to_clusters(cl, rp, g, p_emp, all_db[low], gi + 1, a)[gi + 1]
-                n_all_cl.update(out[0]); n_all_rp.update(out[1]); n_all_db[gi + 1] = out[2]
-            all_cl, all_rp, all_db = n_all_cl, n_all_rp, n_all_db
-            arr = [(v[0], v[1], v[2], v[3], v[4], v[5]) for _, v in sorted(all_rp.items(), key=lambda x: x[1][5], reverse=True)]
-            if len(groups) == 1:
-                break
-        return len(all_cl)
-
-    for _ in range(min(args.warmup, 1)):
-        one_step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_step()
-    dt = time.perf_counter() - t0
-    v = ns * args.steps / dt
-    sample = ("prefix of %d reads (%d per core) of the same score-ordered workload; oracle port of the reference's "
-              "--t %d path: %d batches in a process pool + merge rounds" % (ns, per_core, cores, len(batches)))
-    print(json.dumps({
-        "impl": "reference", "metric": "reads/sec clustered (750 bp ONT amplicons, k=13 w=20, cluster-only)",
-        "value": v, "unit": "reads/s", "n_gpus": max(1, world), "steps": args.steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": dt * 1000.0 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    n_total = cfg["reads_per_gpu"] * world
+    # a prefix of the score-ordered workload is a score-ordered workload: generate the prefix pool only
+    n_pool = min(n_total, 60000)
+    seq, qual, offsets, acc = make_workload(n_pool, args.seed + world - 1, n_species=cfg["species"])
+    r = reference_arm.measure(seq, qual, offsets, acc, K, W, world, args.steps, args.warmup, cores,
+                              budget_s=args.ref_budget, tag="arm")
+    line = {
+        "impl": "reference", "metric": "reads/sec clustered + consensus bp/sec, 750bp ONT amplicons, 1/2/4/8 B200",
+        "value": r["value"], "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "python int/float", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1]: %d synthetic 750 bp ONT-error reads per GPU, 10 species, k=13 w=20, "
-                               "cluster-only" % args.reads, "sample_reads": ns},
-        "cpu_baseline": {"value": v, "unit": "reads/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "config": workload_config(cfg, world),
+        "cpu_baseline": {"value": r["value"], "unit": "reads/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                         "t": r["t"], "copies": r["copies"], "sample_reads": r["sample_reads"],
+                         "one_copy_reads_per_s": r["one_copy_reads_per_s"],
+                         "aligner_seconds_share": r["aligner_seconds_share"], "clusters": r["clusters"],
+                         "pool_note": "the sample is a prefix of a %d-read pool generated like the GPU arm's (same generator, "
+                                      "seed and species; the GPU arm's pool has %d reads)" % (n_pool, n_total)},
+        "e2e": {"value": r["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}
+    print(json.dumps(line))
 
 
 def main():
@@ -618,25 +589,27 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--reads", type=int, default=100000, help="reads per GPU")
+    ap.add_argument("--config", default="auto", choices=["auto", "c1", "c3"])
+    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the configuration's)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--tile", type=int, default=0)
-    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=4000)
-    ap.add_argument("--ref-reads-per-core", dest="ref_reads_per_core", type=int, default=1500)
+    ap.add_argument("--cpu-budget", dest="cpu_budget", type=float, default=15.0)
+    ap.add_argument("--ref-budget", dest="ref_budget", type=float, default=150.0)
     ap.add_argument("--roofline-reads", dest="roofline_reads", type=int, default=2000000)
     ap.add_argument("--no-roofline", dest="no_roofline", action="store_true")
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--no-consensus", dest="no_consensus", action="store_true")
-    ap.add_argument("--abundance-ratio", dest="abundance_ratio", type=float, default=0.02)
-    ap.add_argument("--max-seqs", dest="max_seqs", type=int, default=200, help="--max_seqs_for_consensus of the consensus leg")
-    ap.add_argument("--racon-iter", dest="racon_iter", type=int, default=3)
-    ap.add_argument("--cpu-consensus-reads", dest="cpu_consensus_reads", type=int, default=60)
+    ap.add_argument("--no-modules", dest="no_modules", action="store_true")
+    ap.add_argument("--abundance-ratio", dest="abundance_ratio", type=float, default=None)
+    ap.add_argument("--max-seqs", dest="max_seqs", type=int, default=None, help="--max_seqs_for_consensus of the consensus leg")
+    ap.add_argument("--racon-iter", dest="racon_iter", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
     else:
-        import __graft_entry__ as g
-        g.build()
+        if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+            import __graft_entry__ as g
+            g.build()                                 # up to date on the GPU box (the built library travels)
         run_ours(args)
 
 

@@ -79,62 +79,53 @@ def reads_to_clusters(clusters, representatives, sorted_reads, p_emp_probs, mini
     init_ids = sorted(init_ids)
 
     if todo:
-        local = {}
-        records, accs = [], []
-        for rid in init_ids:
-            t = representatives[rid]
-            local[rid] = len(records)
-            records.append((t[3], t[4]))
-            accs.append(t[2])
-        for (rid, _b, acc, seq, qual, _s) in todo:
-            local[rid] = len(records)
-            records.append((seq, qual))
-            accs.append(acc)
+        # one upload for the table's representatives (first) and the reads to cluster; everything
+        # per read below is done on arrays, Python objects are touched for survivors and moves only
+        n_init, n_todo = len(init_ids), len(todo)
+        init_recs = [representatives[rid] for rid in init_ids]
+        seqs = [t[3] for t in init_recs] + [r[3] for r in todo]
+        quals = [t[4] for t in init_recs] + [r[4] for r in todo]
+        accs = [t[2] for t in init_recs] + [r[2] for r in todo]
+        ids = np.array(init_ids + [r[0] for r in todo], dtype=np.int64)
+        offs = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(np.fromiter(map(len, seqs), np.int64, len(seqs)), out=offs[1:])
         eng = _engine.get_engine(getattr(args, "device", 0))
-        eng.upload_records(records)
+        eng.upload(np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8),
+                   np.frombuffer("".join(quals).encode("ascii"), dtype=np.uint8), offs)
         eng.minimizers(k, w)
         eng.quality_stats()
         max_gap = _engine.max_gap_table(p_emp_probs, args.min_prob_no_hits)
-        order = np.array([local[r[0]] for r in todo], dtype=np.int32)
-        init = np.array([local[r] for r in init_ids], dtype=np.int32)
-        assign, via, stats = eng.cluster(k, w, max_gap, order, _engine.accession_ranks(accs), init_reps=init,
+        assign, via, stats = eng.cluster(k, w, max_gap, np.arange(n_init, n_init + n_todo, dtype=np.int32),
+                                         _engine.accession_ranks(accs), init_reps=np.arange(n_init, dtype=np.int32),
                                          min_shared=args.min_shared, min_fraction=args.min_fraction,
                                          mapped_threshold=args.mapped_threshold,
                                          aligned_threshold=args.aligned_threshold,
                                          symmetric=bool(args.symmetric_map_align_thresholds))
-        err_c, _eu, _bk = eng.get_quality_stats()
-        local_to_id = {v: kk for kk, v in local.items()}
-        new_reps = [i for i, a in enumerate(assign) if a == -1]
-        # minimizers of the new representatives go into the caller's table (cluster.py:328-334)
-        if new_reps:
-            _lc, counts, kmer, pos = eng.get_minimizers()
-            starts = np.zeros(len(counts) + 1, dtype=np.int64)
-            np.cumsum(counts, out=starts[1:])
-        moved = []
-        for i, rec in enumerate(todo):
-            rid, _b, acc, seq, qual, score = rec
-            a = int(assign[i])
-            if a == -2:
-                continue                                      # compressed read shorter than k
+        new_local = np.nonzero(assign == -1)[0]
+        # survivors: 8-tuples (error rate of the compressed qualities, compressed sequence) and their
+        # minimizers into the caller's table (cluster.py:292, 328-334)
+        for i in new_local.tolist():
+            li = n_init + i
+            rid, _b, acc, seq, qual, score = todo[i][:6]
             t = representatives[rid]
             if len(t) == 8:
                 representatives[rid] = t[:1] + (new_batch_index,) + t[2:]
             else:
-                representatives[rid] = (rid, new_batch_index, acc, seq, qual, score,
-                                        float(err_c[local[rid]]), _hpol(seq) if a == -1 else None)
-            if a >= 0:
-                moved.append((rid, local_to_id[a]))
-            else:
-                li = local[rid]
-                for c in kmer[starts[li]:starts[li + 1]]:
-                    m = _engine.decode_kmer(c, k)
-                    s = minimizer_database.get(m)
-                    if s is None:
-                        minimizer_database[m] = s = set()
-                    s.add(rid)
-        for rid, winner in moved:                             # cluster.py:338-345
-            clusters[winner].extend(clusters[rid])
-            del clusters[rid]
+                err_c, _eu, _bk = eng.get_quality_stats(li, li + 1)
+                representatives[rid] = (rid, new_batch_index, acc, seq, qual, score, float(err_c[0]), _hpol(seq))
+            _lc, _cnt, kmer, _pos = eng.get_minimizers(li, li + 1)
+            for c in kmer:
+                m = _engine.decode_kmer(c, k)
+                s = minimizer_database.get(m)
+                if s is None:
+                    minimizer_database[m] = s = set()
+                s.add(rid)
+        # assigned reads join their representative in processing order (cluster.py:338-345)
+        moved = np.nonzero(assign >= 0)[0]
+        winners = ids[assign[moved]].tolist()
+        for i, winner in zip(moved.tolist(), winners):
+            rid = todo[i][0]
+            clusters[winner].extend(clusters.pop(rid))
             del representatives[rid]
         logging.debug("Total number of reads iterated through:{0}".format(len(sorted_reads)))
         logging.debug("Passed mapping criteria:{0}".format(stats["n_mapped"]))

@@ -19,6 +19,7 @@ def main():
     from ngspeciesid_b200 import engine as E
     from ngspeciesid_b200 import multi_gpu as M
 
+    on_gpu = len(sys.argv) > 4 and sys.argv[4] == "gpu"
     dist.init_process_group("gloo")
     ops = GlooOps(dist)
     rank, world = ops.rank, ops.world
@@ -32,7 +33,17 @@ def main():
     bounds = M.batch_bounds(lens, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     mine = ra[lo:hi]
-    engs = [OracleEngine(p_emp, args, ops) for _ in range(4)]
+    if on_gpu:
+        # the product path: real engines, NCCL inside libngsid.so (the id travels over the gloo group)
+        dev = int(os.environ.get("LOCAL_RANK", "0"))
+        engs = [E.Engine(dev) for _ in range(4)]
+        if world > 1:
+            uid = ops.allgather(E.nccl_unique_id() if rank == 0 else None)[0]
+            engs[0].nccl_init(uid, rank, world)
+            for e in engs[1:]:
+                e.nccl_share(engs[0])
+    else:
+        engs = [OracleEngine(p_emp, args, ops) for _ in range(4)]
     engs[0].upload_records([(r[3], r[4]) for r in mine])
     pipe = M.Pipeline(*engs, rank=rank, world=world, k=args.k, w=args.w)
     roots = pipe.cluster(E.max_gap_table(p_emp, args.min_prob_no_hits), [r[2] for r in mine], [r[5] for r in mine],

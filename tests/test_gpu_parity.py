@@ -333,6 +333,23 @@ def test_rank_sharded_driver_on_gpu(p_table):
         dist.destroy_process_group()
 
 
+def _merge_representatives(bench, eng2, seq, qual, offsets, acc, gathered, params):
+    """gathered[b] = global read ids of the representatives batch b ended with: uploads these reads
+    only and runs the merge rounds on them -> ({merged representative: winner}, final representatives)."""
+    from ngspeciesid_b200 import engine as E
+    ids = sorted(set(x for g in gathered for x in g))
+    idx = {g: i for i, g in enumerate(ids)}
+    parts = [bench.slice_reads(seq, qual, offsets, g, g + 1) for g in ids]
+    m_off = np.zeros(len(ids) + 1, dtype=np.int64)
+    np.cumsum([len(p[0]) for p in parts], out=m_off[1:])
+    eng2.upload(np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]), m_off)
+    eng2.minimizers(13, 20)
+    eng2.quality_stats()
+    ar = E.accession_ranks([acc[g] for g in ids])
+    merges, final = bench.merge_rounds(eng2, params, ar, {b + 1: [idx[x] for x in g] for b, g in enumerate(gathered)}, len(gathered))
+    return {ids[a]: ids[b] for a, b in merges.items()}, [ids[i] for i in final]
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_bench_batches_and_merge_rounds_match_t_n(world, p_table):
     """bench.py's N-GPU decomposition (batch_bounds -> one clustering pass per batch -> ids-only
@@ -368,7 +385,7 @@ def test_bench_batches_and_merge_rounds_match_t_n(world, p_table):
                 if a != -2:
                     rep_of[lo + i] = lo + i if a == -1 else lo + int(a)
             gathered.append([lo + i for i in np.nonzero(assign == -1)[0]])
-        merges, final = bench.merge_representatives(eng2, seq, qual, off, acc, gathered, params)
+        merges, final = _merge_representatives(bench, eng2, seq, qual, off, acc, gathered, params)
     finally:
         eng.close(); eng2.close()
 
