@@ -39,11 +39,14 @@ const char *ngsid_last_error(const ngsid_ctx *ctx);   /* valid until the next ca
 int ngsid_version(void);                               /* ABI version, currently 1 */
 /* Number of kernels this context has launched since creation / since the last reset. */
 int64_t ngsid_launch_count(const ngsid_ctx *ctx);
+/* DP cells (graph rows x layer bases, summed over layers and jobs) of the last ngsid_poa_consensus. */
+int64_t ngsid_poa_cells(const ngsid_ctx *ctx);
 void ngsid_reset_launch_count(ngsid_ctx *ctx);
 int ngsid_sync(ngsid_ctx *ctx);
 /* Device time (CUDA events on the context's stream) of the most recent run of a phase, in ms:
  * which = 0 pack (inside upload), 1 K1 minimizers, 2 K0 quality stats, 3 whole clustering pass,
- * 4 sum of K4 launches inside the last clustering pass, 5 sum of map launches inside it.
+ * 4 sum of K4 launches inside the last clustering pass, 5 sum of map launches inside it;
+ * last ngsid_poa_consensus call (host clock): 6 kernels + copies, 7 host graph work, 8 whole call.
  * Returns a negative value when that phase has not run.                                        */
 float ngsid_phase_ms(ngsid_ctx *ctx, int which);
 /* Tuning / test switches. option 1 selects the K1 kernel: 0 (default) the stream kernel for
@@ -189,24 +192,21 @@ int ngsid_fastq_parse(const uint8_t *buf, int64_t len, int64_t cap_records,
  * match 5, mismatch -4, linear gap -2, quality weights, heaviest-bundle consensus) and the
  * per-window POA inside racon (consensus.run_racon, modules/consensus.py:107-126: global,
  * 3 / -5 / -4, backbone without weight, coverage-trimmed consensus).
- * Jobs are independent (one thread block each). Job j consists of layers
- * [job_off[j], job_off[j+1]) added in that order; layer l is bases [layer_begin[l],
- * layer_begin[l]+layer_len[l]) of uploaded read layer_src[l] (weights = quality - 33) or, when
- * layer_src[l] < 0, of auxiliary sequence -layer_src[l]-1 (weight 0).
- * out_seq holds n_jobs rows of out_stride bytes; out_len[j] = consensus length.
- * max_nodes bounds the graph of one job (0 = 32 x longest layer, at least 4096); a job that would
- * exceed it fails the call with NGSID_EUNSUPPORTED (no silent truncation).                      */
+ * Job j consists of layers [job_off[j], job_off[j+1]) added in that order; layer l is bases
+ * [layer_begin[l], layer_begin[l]+layer_len[l]) of uploaded read layer_src[l] (weights =
+ * quality - 33) or, when layer_src[l] < 0, of auxiliary sequence -layer_src[l]-1 (weight 0).
+ * All DP cells and the traceback run on the GPU, one launch per layer step over every job that
+ * still has a layer (one thread block per job); the graph of a job -- adding the alignment and
+ * spoa's depth-first topological re-sort, O(V + E) pointer chasing -- is kept on host threads
+ * inside the library. Graphs grow as needed: max_nodes > 0 makes a larger graph an error
+ * (NGSID_EUNSUPPORTED), 0 = no bound. Layers are limited to 4095 bases.
+ * out_seq holds n_jobs rows of out_stride bytes; out_len[j] = consensus length.                   */
 typedef struct {
     int32_t mode;        /* 0 local (spoa -l 0), 1 global (racon windows) */
     int32_t match, mismatch, gap;
     int32_t trim;        /* racon's coverage trimming of the consensus ends */
     int32_t max_nodes;
-    int32_t reserved[2]; /* [1]: kernel shape, 0 = wavefront kernel (falls back to the row kernel
-                          * when a graph outgrows its shared-memory ring), 1 = row kernel.
-                          * [0]: 0 = spoa's depth-first re-sort after every layer (both kernels);
-                          * 1 = experimental path-insertion order, row kernel only (not a valid
-                          * topological order once aligned alternates are reused -- kept for the
-                          * oracle comparison, never used by modules/).                          */
+    int32_t reserved[2];
 } ngsid_poa_params;
 
 int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libngsid.so")
 
 EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last_error",
-           "ngsid_launch_count", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
+           "ngsid_launch_count", "ngsid_poa_cells", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
            "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus",
            "ngsid_fastq_parse", "ngsid_nccl_unique_id", "ngsid_nccl_init", "ngsid_nccl_finalize", "ngsid_nccl_share", "ngsid_allgather_bytes",
@@ -63,6 +63,8 @@ def load():
     lib.ngsid_last_error.restype = ctypes.c_char_p
     lib.ngsid_launch_count.argtypes = [vp]
     lib.ngsid_launch_count.restype = i64
+    lib.ngsid_poa_cells.argtypes = [vp]
+    lib.ngsid_poa_cells.restype = i64
     lib.ngsid_reset_launch_count.argtypes = [vp]
     lib.ngsid_reset_launch_count.restype = None
     lib.ngsid_sync.argtypes = [vp]

@@ -8,7 +8,7 @@ SRC = os.path.join(HERE, "csrc", "ngsid_api.cu")
 OUT = os.path.join(HERE, "libngsid.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "--fmad=false", "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-ldl"]
+         "--fmad=false", "-Xcompiler", "-fPIC,-fopenmp", "-shared", "-Xptxas", "-v", "-ldl", "-lgomp"]
 
 
 def sources():

@@ -1,0 +1,319 @@
+// Host side of K5 (see k5_rows.cuh): graphs of all jobs on the host, one kernel launch per layer step
+// over every job that still has a layer, graph update + spoa's re-sort on host threads in between.
+#pragma once
+#include <omp.h>
+#include <chrono>
+#include <thread>
+#include "k5_rows.cuh"
+
+namespace k5host {
+
+// ---- pinned host staging that only grows
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostGraph {
+    std::vector<uint8_t> mem;
+    PoaGraph G;
+    int Lmax = 1;
+    bool init = false;
+    void alloc(int Vcap, int lmax) {
+        const int Ecap = Vcap * 4, Acap = Vcap * 8, Scap = Ecap + Acap + Vcap + 64;
+        Lmax = lmax;
+        mem.assign(poa_graph_bytes(Vcap, Ecap, Acap, Scap, lmax) + 64, 0);
+        poa_graph_bind(G, mem.data(), Vcap, Ecap, Acap, Scap, lmax);
+        init = true;
+    }
+    // room for one more layer of L bases (every base may add a node, two edges, six aligned entries)
+    void reserve(int L) {
+        if (!init) { alloc(std::max(2048, 4 * L + 64), L); return; }
+        if (G.V + L + 2 <= G.Vcap && G.E + 2 * L + 4 <= G.Ecap && G.A + 8 * L + 8 <= G.Acap && L <= Lmax) return;
+        int Vcap = G.Vcap;
+        while (G.V + L + 2 > Vcap || G.E + 2 * L + 4 > Vcap * 4 || G.A + 8 * L + 8 > Vcap * 8) Vcap *= 2;
+        HostGraph n;
+        n.alloc(Vcap, std::max(L, Lmax));
+        poa_graph_copy(n.G, G);
+        mem.swap(n.mem);
+        G = n.G;
+        Lmax = n.Lmax;
+    }
+};
+
+struct Layer { const uint8_t *s; const uint8_t *q; int L; int64_t arena_off; };
+
+// rows of the graph in topological order for the kernel; returns the number of overflow entries
+static int64_t build_rows(const PoaGraph &G, int ring, uint4 *rows, int32_t *ovf, bool count_only, int *max_np)
+{
+    int64_t n_ovf = 0;
+    for (int r = 0; r < G.V; ++r) {
+        const int v = G.order[r];
+        int np = 0;
+        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) ++np;
+        if (np > *max_np) *max_np = np;
+        if (count_only) { if (np > 3) n_ovf += np; continue; }
+        uint4 m = make_uint4((uint32_t)G.letter[v] | ((uint32_t)std::min(np, 255) << 8) | (G.out_head[v] < 0 ? K5R_FLAG_SINK : 0u), 0u, 0u, 0u);
+        int u = 0;
+        if (np > 3) m.y = (uint32_t)n_ovf;
+        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e], ++u) {
+            const int p = G.rank[G.e_from[e]] + 1;
+            if (np > 3) ovf[n_ovf + u] = p;
+            else if (u == 0) m.y = (uint32_t)p; else if (u == 1) m.z = (uint32_t)p; else m.w = (uint32_t)p;
+            if ((r + 1) - p >= ring) rows[p - 1].x |= K5R_FLAG_STORE;        // a far successor reads it from global memory
+        }
+        if (np > 3) n_ovf += np;
+        rows[r] = m;
+    }
+    return n_ovf;
+}
+
+__global__ void k_gather_layers(const uint8_t *__restrict__ seq, const uint8_t *__restrict__ qual, const int64_t *__restrict__ off,
+                                const uint8_t *__restrict__ aux, const int64_t *__restrict__ aoff,
+                                const int32_t *__restrict__ src, const int32_t *__restrict__ beg, const int32_t *__restrict__ len,
+                                const int64_t *__restrict__ lay_off, int64_t n_layers, uint8_t *__restrict__ o_seq, uint8_t *__restrict__ o_qual)
+{
+    const int64_t wi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wi >= n_layers) return;
+    const uint32_t lane = lane_id();
+    const int sr = src[wi], b = beg[wi], L = len[wi];
+    const uint8_t *s = (sr >= 0 ? seq + off[sr] : aux + aoff[-sr - 1]) + b;
+    const uint8_t *q = sr >= 0 ? qual + off[sr] + b : nullptr;
+    uint8_t *os = o_seq + lay_off[wi], *oq = o_qual + lay_off[wi];
+    for (int i = lane; i < L; i += 32) { os[i] = s[i]; oq[i] = q ? q[i] : (uint8_t)33; }
+}
+
+}  // namespace k5host
+
+static int host_threads(const ngsid_ctx *ctx)
+{
+    if (const char *e = getenv("NGSID_HOST_THREADS")) return std::max(1, atoi(e));
+    const int hw = (int)std::thread::hardware_concurrency();
+    const int ranks = ctx->nccl_comm ? std::max(1, ctx->nccl_nranks) : 1;
+    return std::max(1, std::min(16, (hw > 0 ? hw : 4) / ranks));
+}
+
+extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                                   const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                                   const int32_t *layer_len, const uint8_t *aux_seq, const int64_t *aux_off,
+                                   int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                                   int32_t *out_nodes)
+{
+    using namespace k5host;
+    if (!ctx || !params || n_jobs < 0) return NGSID_EINVAL;
+    if (n_jobs == 0) return NGSID_OK;
+    if (!job_off || !layer_src || !layer_begin || !layer_len || !out_seq || !out_len || out_stride < 1) return NGSID_EINVAL;
+    if (params->gap >= 0) return fail(ctx, NGSID_EINVAL, "gap must be negative");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int64_t n_layers = job_off[n_jobs];
+    int Lmax = 1;
+    std::vector<int64_t> lay_off((size_t)n_layers + 1, 0);
+    int64_t max_job_layers = 0;
+    for (int64_t j = 0; j < n_jobs; ++j) max_job_layers = std::max(max_job_layers, job_off[j + 1] - job_off[j]);
+    for (int64_t l = 0; l < n_layers; ++l) {
+        const int src = layer_src[l];
+        int64_t len;
+        if (src >= 0) { if (src >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "layer read out of range"); len = ctx->h_off[src + 1] - ctx->h_off[src]; }
+        else { int64_t x = -(int64_t)src - 1; if (x >= n_aux) return fail(ctx, NGSID_EINVAL, "layer aux out of range"); len = aux_off[x + 1] - aux_off[x]; }
+        if (layer_begin[l] < 0 || layer_len[l] < 0 || (int64_t)layer_begin[l] + layer_len[l] > len) return fail(ctx, NGSID_EINVAL, "layer range out of bounds");
+        Lmax = std::max(Lmax, (int)layer_len[l]);
+        lay_off[l + 1] = lay_off[l] + ((layer_len[l] + 15) & ~15);
+    }
+    if (Lmax + 1 > K5R_MAXW * K5R_TILE) return fail(ctx, NGSID_EUNSUPPORTED, "POA layer longer than 4095 bases");
+    int rc = upload_aux(ctx, aux_seq, aux_off, n_aux);
+    if (rc) return rc;
+
+    // ---- bases + qualities of every layer: one arena on the device (read by the DP) and on the host (graph update)
+    const size_t arena = (size_t)lay_off[n_layers] + 64;
+    static thread_local PinBuf pin_lay, pin_meta, pin_path;
+    CUDA_TRY(ctx, ctx->d_poa_arena.ensure(2 * arena));
+    CUDA_TRY(ctx, pin_lay.ensure(2 * arena));
+    CUDA_TRY(ctx, ctx->d_lsrc.ensure((size_t)n_layers * 4 + 16));
+    CUDA_TRY(ctx, ctx->d_lbeg.ensure((size_t)n_layers * 4 + 16));
+    CUDA_TRY(ctx, ctx->d_llen.ensure((size_t)n_layers * 4 + 16));
+    CUDA_TRY(ctx, ctx->d_job_off.ensure((size_t)(n_layers + 1) * 8));
+    uint8_t *d_lseq = ctx->d_poa_arena.as<uint8_t>(), *d_lqual = d_lseq + arena;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lsrc.p, layer_src, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lbeg.p, layer_begin, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_llen.p, layer_len, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_job_off.p, lay_off.data(), (size_t)(n_layers + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_layers) {
+        k_gather_layers<<<(unsigned)((n_layers + 7) / 8), 256, 0, ctx->stream>>>(
+            ctx->d_seq.as<uint8_t>(), ctx->d_qual.as<uint8_t>(), ctx->d_off.as<int64_t>(),
+            n_aux > 0 ? ctx->d_auxseq.as<uint8_t>() : nullptr, n_aux > 0 ? ctx->d_aoff.as<int64_t>() : nullptr,
+            ctx->d_lsrc.as<int32_t>(), ctx->d_lbeg.as<int32_t>(), ctx->d_llen.as<int32_t>(), ctx->d_job_off.as<int64_t>(),
+            n_layers, d_lseq, d_lqual);
+        KERNEL_CHECK(ctx);
+        CUDA_TRY(ctx, cudaMemcpyAsync(pin_lay.p, d_lseq, 2 * arena, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint8_t *h_lseq = pin_lay.as<uint8_t>(), *h_lqual = h_lseq + arena;
+
+    const auto t_call = std::chrono::steady_clock::now();
+    double ms_dev = 0.0, ms_host = 0.0;
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const int T = host_threads(ctx);
+    const int ring = (Lmax + 1 <= 8 * K5R_TILE) ? 16 : ((Lmax + 1 <= 16 * K5R_TILE) ? 8 : 4);
+    std::vector<HostGraph> graphs((size_t)n_jobs);
+    std::vector<int> jerr((size_t)n_jobs, 0);
+    std::vector<int32_t> dp_jobs;                     // jobs that run the DP in this step
+    std::vector<K5RJob> desc;
+    std::vector<int64_t> n_ovf_of((size_t)n_jobs, 0);
+    CUDA_TRY(ctx, ctx->d_poa_err.ensure(64));
+    const int max_nodes = params->max_nodes;
+    int64_t total_cells = 0;
+
+    for (int64_t step = 0; step < max_job_layers; ++step) {
+        // ---- layers that need no DP (first layer of a job, empty layers) go straight into the graph
+        auto t_h = std::chrono::steady_clock::now();
+        dp_jobs.clear();
+        for (int64_t j = 0; j < n_jobs; ++j) {
+            if (jerr[j] || job_off[j] + step >= job_off[j + 1]) continue;
+            const int64_t l = job_off[j] + step;
+            const int L = layer_len[l];
+            HostGraph &hg = graphs[j];
+            hg.reserve(std::max(L, 1));
+            if (hg.G.V == 0 || L == 0) {
+                const uint8_t *q = layer_src[l] >= 0 ? h_lqual + lay_off[l] : nullptr;
+                poa_add_alignment(hg.G, 0, h_lseq + lay_off[l], q, L);
+                if (hg.G.err) jerr[j] = hg.G.err;
+            } else dp_jobs.push_back((int32_t)j);
+        }
+        const int nd = (int)dp_jobs.size();
+        if (nd == 0) { ms_host += since(t_h); continue; }
+        // ---- sizes
+        int Lstep = 1, max_np = 0;
+        std::vector<int> np_max((size_t)nd, 0);
+#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+        for (int x = 0; x < nd; ++x) {
+            const int j = dp_jobs[x];
+            n_ovf_of[j] = build_rows(graphs[j].G, ring, nullptr, nullptr, true, &np_max[x]);
+        }
+        desc.assign((size_t)nd, K5RJob());
+        int64_t meta_n = 0, ovf_n = 0, mat_n = 0, path_n = 0;
+        for (int x = 0; x < nd; ++x) {
+            const int j = dp_jobs[x];
+            const int64_t l = job_off[j] + step;
+            Lstep = std::max(Lstep, (int)layer_len[l]);
+            max_np = std::max(max_np, np_max[x]);
+        }
+        if (max_np > K5R_MAXE) return fail(ctx, NGSID_EUNSUPPORTED, "a graph node has more than 119 in-edges");
+        const int NW = (Lstep + 1 + K5R_TILE - 1) / K5R_TILE;
+        const int ld = NW * K5R_TILE;
+        for (int x = 0; x < nd; ++x) {
+            const int j = dp_jobs[x];
+            const int64_t l = job_off[j] + step;
+            const PoaGraph &G = graphs[j].G;
+            K5RJob &D = desc[x];
+            D.V = G.V; D.L = layer_len[l]; D.mode = params->mode;
+            D.match = params->match; D.mismatch = params->mismatch; D.gap = params->gap;
+            D.seq_off = lay_off[l];
+            D.meta_off = meta_n; meta_n += G.V;
+            D.ovf_off = ovf_n; ovf_n += n_ovf_of[j];
+            D.mat_off = mat_n; mat_n += (int64_t)(G.V + 1) * ld;
+            D.path_off = path_n; path_n += G.V + D.L + 2;
+            total_cells += (int64_t)G.V * D.L;
+            if (max_nodes > 0 && G.V > max_nodes) return fail(ctx, NGSID_EUNSUPPORTED, "POA graph larger than max_nodes");
+        }
+        // ---- rows of every graph into pinned memory, then to the device
+        const size_t b_desc = ((size_t)nd * sizeof(K5RJob) + 255) & ~(size_t)255;
+        const size_t b_meta = ((size_t)meta_n * 16 + 255) & ~(size_t)255;
+        const size_t b_ovf = ((size_t)ovf_n * 4 + 255) & ~(size_t)255;
+        CUDA_TRY(ctx, pin_meta.ensure(b_desc + b_meta + b_ovf));
+        uint8_t *hm = pin_meta.as<uint8_t>();
+        memcpy(hm, desc.data(), (size_t)nd * sizeof(K5RJob));
+        uint4 *h_rows = reinterpret_cast<uint4 *>(hm + b_desc);
+        int32_t *h_ovf = reinterpret_cast<int32_t *>(hm + b_desc + b_meta);
+#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+        for (int x = 0; x < nd; ++x) {
+            int dummy = 0;
+            build_rows(graphs[dp_jobs[x]].G, ring, h_rows + desc[x].meta_off, h_ovf + desc[x].ovf_off, false, &dummy);
+        }
+        ms_host += since(t_h);
+        auto t_d = std::chrono::steady_clock::now();
+        CUDA_TRY(ctx, ctx->d_poa_meta.ensure(b_desc + b_meta + b_ovf));
+        CUDA_TRY(ctx, ctx->d_poa_h.ensure((size_t)mat_n * 4 + 256));
+        CUDA_TRY(ctx, ctx->d_poa_dir.ensure((size_t)mat_n + 256));
+        CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)path_n * 8 + (size_t)nd * 16 + 256));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_poa_meta.p, hm, b_desc + b_meta + b_ovf, cudaMemcpyHostToDevice, ctx->stream));
+        int32_t *d_out = reinterpret_cast<int32_t *>(ctx->d_poa_out.as<uint8_t>() + (size_t)path_n * 8);
+        CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, (size_t)nd * 16, ctx->stream));
+        K5RArgs A;
+        A.jobs = ctx->d_poa_meta.as<K5RJob>();
+        A.layers = d_lseq;
+        A.meta = reinterpret_cast<const uint4 *>(ctx->d_poa_meta.as<uint8_t>() + b_desc);
+        A.ovf = reinterpret_cast<const int32_t *>(ctx->d_poa_meta.as<uint8_t>() + b_desc + b_meta);
+        A.H = ctx->d_poa_h.as<int32_t>(); A.DIR = ctx->d_poa_dir.as<uint8_t>();
+        A.path = ctx->d_poa_out.as<int2>(); A.out = d_out; A.ld = ld; A.ring = ring;
+        const size_t smem = k5r_smem_bytes(NW, ring);
+#define K5R_LAUNCH(MODE, MAXT)                                                                                     \
+        do {                                                                                                       \
+            CUDA_TRY(ctx, cudaFuncSetAttribute(k5r_layer_kernel<MODE, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k5r_layer_kernel<MODE, MAXT><<<nd, NW * 32, smem, ctx->stream>>>(A);                                   \
+        } while (0)
+        if (params->mode) { if (NW <= 8) K5R_LAUNCH(1, 256); else K5R_LAUNCH(1, 1024); }
+        else { if (NW <= 8) K5R_LAUNCH(0, 256); else K5R_LAUNCH(0, 1024); }
+#undef K5R_LAUNCH
+        KERNEL_CHECK(ctx);
+        CUDA_TRY(ctx, pin_path.ensure((size_t)path_n * 8 + (size_t)nd * 16));
+        CUDA_TRY(ctx, cudaMemcpyAsync(pin_path.p, ctx->d_poa_out.p, (size_t)path_n * 8 + (size_t)nd * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        ms_dev += since(t_d);
+        t_h = std::chrono::steady_clock::now();
+        const int2 *h_path = pin_path.as<int2>();
+        const int32_t *h_out = reinterpret_cast<const int32_t *>(pin_path.as<uint8_t>() + (size_t)path_n * 8);
+        // ---- graph update + re-sort on host threads
+#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+        for (int x = 0; x < nd; ++x) {
+            const int j = dp_jobs[x];
+            const int64_t l = job_off[j] + step;
+            PoaGraph &G = graphs[j].G;
+            if (h_out[x * 4 + 2]) { jerr[j] = h_out[x * 4 + 2]; continue; }
+            const int n = h_out[x * 4];
+            const int2 *pp = h_path + desc[x].path_off;
+            for (int t = 0; t < n; ++t) {
+                G.aln_node[t] = pp[t].x > 0 ? G.order[pp[t].x - 1] : -1;
+                G.aln_pos[t] = pp[t].y;
+            }
+            const uint8_t *q = layer_src[l] >= 0 ? h_lqual + lay_off[l] : nullptr;
+            poa_add_alignment(G, n, h_lseq + lay_off[l], q, layer_len[l]);
+            if (G.err) jerr[j] = G.err;
+        }
+        ms_host += since(t_h);
+    }
+    // ---- heaviest bundle per job
+    int worst = 0;
+#pragma omp parallel for num_threads(T) schedule(dynamic, 1)
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        int len = -1;
+        if (!jerr[j]) {
+            if (graphs[j].init) len = poa_consensus(graphs[j].G, params->trim, out_seq + (size_t)j * out_stride, (int)out_stride);
+            else len = 0;
+            if (len < 0) jerr[j] = 5;
+        }
+        out_len[j] = len;
+        if (out_nodes) out_nodes[j] = graphs[j].init ? graphs[j].G.V : 0;
+    }
+    for (int64_t j = 0; j < n_jobs; ++j) worst = std::max(worst, jerr[j]);
+    ctx->poa_cells = total_cells;
+    ctx->poa_ms[0] = (float)ms_dev; ctx->poa_ms[1] = (float)ms_host; ctx->poa_ms[2] = (float)since(t_call);
+    if (worst) {
+        char msg[160];
+        snprintf(msg, sizeof msg, "POA failed (code %d: 1-3 graph capacity, 5 output buffer, 7 in-edges, 8 no end cell)", worst);
+        return fail(ctx, NGSID_EUNSUPPORTED, msg);
+    }
+    return NGSID_OK;
+}

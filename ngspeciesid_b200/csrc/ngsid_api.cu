@@ -11,8 +11,6 @@
 #include "k2_map.cuh"
 #include "k4_align.cuh"
 #include "k4_trace.cuh"
-#include "k5_poa.cuh"
-#include "k5_wave.cuh"
 
 static const size_t SMEM_BUDGET = 200 * 1024;
 
@@ -51,7 +49,8 @@ extern "C" int ngsid_ctx_create(int device_id, ngsid_ctx **out)
 
 extern "C" float ngsid_phase_ms(ngsid_ctx *ctx, int which)
 {
-    if (!ctx || which < 0 || which > 5) return -1.f;
+    if (!ctx || which < 0 || which > 8) return -1.f;
+    if (which >= 6) return ctx->poa_ms[which - 6];
     if (which >= 4) return ctx->pev_valid[which] ? ctx->phase_acc[which] : -1.f;
     if (!ctx->pev_valid[which]) return -1.f;
     float ms = -1.f;
@@ -108,6 +107,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
 
 extern "C" const char *ngsid_last_error(const ngsid_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int64_t ngsid_launch_count(const ngsid_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t ngsid_poa_cells(const ngsid_ctx *ctx) { return ctx ? ctx->poa_cells : 0; }
 extern "C" void ngsid_reset_launch_count(ngsid_ctx *ctx) { if (ctx) ctx->launches = 0; }
 extern "C" int ngsid_sync(ngsid_ctx *ctx)
 {
@@ -652,139 +652,7 @@ extern "C" int ngsid_sg_align_paths(ngsid_ctx *ctx, const int32_t *a, const int3
 
 
 // ================================================================================ K5
-extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
-                                   const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
-                                   const int32_t *layer_len, const uint8_t *aux_seq, const int64_t *aux_off,
-                                   int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
-                                   int32_t *out_nodes)
-{
-    if (!ctx || !params || n_jobs < 0) return NGSID_EINVAL;
-    if (n_jobs == 0) return NGSID_OK;
-    if (!job_off || !layer_src || !layer_begin || !layer_len || !out_seq || !out_len || out_stride < 1) return NGSID_EINVAL;
-    if (params->gap >= 0) return fail(ctx, NGSID_EINVAL, "gap must be negative");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const int64_t n_layers = job_off[n_jobs];
-    int Lmax = 1;
-    for (int64_t l = 0; l < n_layers; ++l) {
-        const int src = layer_src[l];
-        int64_t len;
-        if (src >= 0) { if (src >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "layer read out of range"); len = ctx->h_off[src + 1] - ctx->h_off[src]; }
-        else { int64_t x = -(int64_t)src - 1; if (x >= n_aux) return fail(ctx, NGSID_EINVAL, "layer aux out of range"); len = aux_off[x + 1] - aux_off[x]; }
-        if (layer_begin[l] < 0 || layer_len[l] < 0 || (int64_t)layer_begin[l] + layer_len[l] > len) return fail(ctx, NGSID_EINVAL, "layer range out of bounds");
-        Lmax = std::max(Lmax, (int)layer_len[l]);
-    }
-    if (Lmax > K5_MAXC * K5_THREADS) return fail(ctx, NGSID_EUNSUPPORTED, "POA layer longer than 4096 bases");
-    int rc = upload_aux(ctx, aux_seq, aux_off, n_aux);
-    if (rc) return rc;
-    const int Vcap = params->max_nodes > 0 ? std::max(params->max_nodes, Lmax + 16) : std::max(4096, 32 * Lmax);
-    const int Ecap = Vcap * 6, Acap = Vcap * 6, Scap = Vcap * 14;
-    const size_t gbytes = (poa_graph_bytes(Vcap, Ecap, Acap, Scap, Lmax) + 255) / 256 * 256;
-    const size_t h_words = ((size_t)(Vcap + 1) * (size_t)(Lmax + 1) + 63) / 64 * 64;
-    int slots = (int)std::min<int64_t>(n_jobs, ctx->sm_count);
-    // keep the DP arenas within 48 GB
-    while (slots > 1 && (double)slots * (double)(h_words * 4 + gbytes) > 48e9) slots /= 2;
-    CUDA_TRY(ctx, ctx->d_poa_arena.ensure(gbytes * slots));
-    CUDA_TRY(ctx, ctx->d_poa_h.ensure(h_words * 4 * slots));
-    CUDA_TRY(ctx, ctx->d_poa_meta.ensure((size_t)Vcap * 4 * K5W_FAST * slots + 64));    // row kernel: 20 B per row; wavefront kernel: K5W_FAST ints
-    CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)n_jobs * out_stride));
-    CUDA_TRY(ctx, ctx->d_poa_len.ensure((size_t)n_jobs * 4));
-    CUDA_TRY(ctx, ctx->d_poa_nodes.ensure((size_t)n_jobs * 4));
-    CUDA_TRY(ctx, ctx->d_poa_err.ensure(64));
-    CUDA_TRY(ctx, ctx->d_job_off.ensure((size_t)(n_jobs + 1) * 8));
-    CUDA_TRY(ctx, ctx->d_lsrc.ensure((size_t)n_layers * 4 + 16));
-    CUDA_TRY(ctx, ctx->d_lbeg.ensure((size_t)n_layers * 4 + 16));
-    CUDA_TRY(ctx, ctx->d_llen.ensure((size_t)n_layers * 4 + 16));
-    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_poa_err.p, 0, 64, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_job_off.p, job_off, (size_t)(n_jobs + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lsrc.p, layer_src, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_lbeg.p, layer_begin, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_llen.p, layer_len, (size_t)n_layers * 4, cudaMemcpyHostToDevice, ctx->stream));
-    K5Args A;
-    A.n_jobs = n_jobs; A.job_off = ctx->d_job_off.as<int64_t>();
-    A.layer_src = ctx->d_lsrc.as<int32_t>(); A.layer_begin = ctx->d_lbeg.as<int32_t>(); A.layer_len = ctx->d_llen.as<int32_t>();
-    A.seq = ctx->d_seq.as<uint8_t>(); A.qual = ctx->d_qual.as<uint8_t>(); A.off = ctx->d_off.as<int64_t>();
-    A.aux = n_aux > 0 ? ctx->d_auxseq.as<uint8_t>() : nullptr; A.aoff = n_aux > 0 ? ctx->d_aoff.as<int64_t>() : nullptr;
-    A.mode = params->mode; A.m = params->match; A.x = params->mismatch; A.g = params->gap; A.trim = params->trim;
-    A.arena = ctx->d_poa_arena.as<uint8_t>(); A.graph_bytes = gbytes;
-    A.Vcap = Vcap; A.Ecap = Ecap; A.Acap = Acap; A.Scap = Scap; A.Lmax = Lmax;
-    A.H = ctx->d_poa_h.as<int32_t>(); A.h_words = h_words;
-    A.rmeta_all = ctx->d_poa_meta.as<int4>();
-    A.rinfo_all = reinterpret_cast<uint32_t *>(ctx->d_poa_meta.as<uint8_t>() + (size_t)Vcap * 16 * slots);
-    A.out = ctx->d_poa_out.as<uint8_t>(); A.out_stride = out_stride; A.out_len = ctx->d_poa_len.as<int32_t>();
-    A.out_nodes = ctx->d_poa_nodes.as<int32_t>(); A.err = ctx->d_poa_err.as<int32_t>();
-    A.cycles = nullptr;
-    if (getenv("NGSID_POA_CYCLES")) {
-        CUDA_TRY(ctx, ctx->d_win.ensure((size_t)n_jobs * 32));
-        A.cycles = ctx->d_win.as<long long>();
-    }
-    // shape: reserved[1] = 0 wavefront kernel (falls back to the row kernel when a graph outgrows
-    // its shared-memory ring), 1 row kernel. Topological order: spoa's re-sort after every layer;
-    // the row kernel can also run the experimental path-insertion rule (reserved[0] = 1).
-    bool use_wave = params->reserved[1] != 1;
-    A.order_mode = params->reserved[0] == 1 ? 1 : 0;
-    int err = 0;
-    if (use_wave) {
-        const size_t dir_bytes = (((size_t)(Vcap + 1) * (size_t)(Lmax + 1)) + 255) / 256 * 256;
-        CUDA_TRY(ctx, ctx->d_poa_dir.ensure(dir_bytes * slots));
-        K5WArgs Wa;
-        Wa.a = A;
-        Wa.dir = ctx->d_poa_dir.as<uint8_t>(); Wa.dir_bytes = dir_bytes;
-        size_t wave_smem = 200 * 1024;
-        if (const char *e = getenv("NGSID_K5W_SMEM_KB")) wave_smem = std::min<size_t>(wave_smem, (size_t)std::max(8, atoi(e)) * 1024);   // tests: force the fallback
-        Wa.smem_words = (int)(wave_smem / 4);
-        if (params->mode) {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
-            k5w_poa_kernel<1><<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);
-        } else {
-            CUDA_TRY(ctx, cudaFuncSetAttribute(k5w_poa_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wave_smem));
-            k5w_poa_kernel<0><<<slots, K5W_THREADS, wave_smem, ctx->stream>>>(Wa);
-        }
-        KERNEL_CHECK(ctx);
-        CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (err == 6 || err == 7) {                 // ring too small / too many in-edges: row kernel
-            use_wave = false;
-            err = 0;
-            CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_poa_err.p, 0, 64, ctx->stream));
-        }
-    }
-    if (!use_wave) {
-    int ring_rows = (int)std::max<size_t>(2, std::min<size_t>(64, (size_t)(160 * 1024) / ((size_t)(Lmax + 2) * sizeof(int))));
-    A.ring_rows = ring_rows;
-    const size_t k5_smem = (size_t)ring_rows * (Lmax + 2) * sizeof(int);
-    const int cneed = (Lmax + K5_THREADS - 1) / K5_THREADS;
-#define K5_LAUNCH(CM)                                                                                        \
-    do {                                                                                                     \
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k5_poa_kernel<CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k5_smem)); \
-        k5_poa_kernel<CM><<<slots, K5_THREADS, k5_smem, ctx->stream>>>(A);                                   \
-    } while (0)
-    if (cneed <= 2) K5_LAUNCH(2);
-    else if (cneed <= 4) K5_LAUNCH(4);
-    else if (cneed <= 8) K5_LAUNCH(8);
-    else K5_LAUNCH(16);
-#undef K5_LAUNCH
-    KERNEL_CHECK(ctx);
-    }
-    CUDA_TRY(ctx, cudaMemcpyAsync(&err, ctx->d_poa_err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_seq, ctx->d_poa_out.p, (size_t)n_jobs * out_stride, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out_len, ctx->d_poa_len.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_nodes) CUDA_TRY(ctx, cudaMemcpyAsync(out_nodes, ctx->d_poa_nodes.p, (size_t)n_jobs * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (A.cycles) {
-        std::vector<long long> cyc((size_t)n_jobs * 4);
-        cudaMemcpy(cyc.data(), A.cycles, cyc.size() * 8, cudaMemcpyDeviceToHost);
-        long long tot[4] = {0, 0, 0, 0};
-        for (int64_t j = 0; j < n_jobs; ++j) for (int q = 0; q < 4; ++q) tot[q] += cyc[j * 4 + q];
-        fprintf(stderr, "[k5] jobs %lld layers %lld: cycles dp %.3g traceback %.3g update+sort %.3g consensus %.3g\n",
-                (long long)n_jobs, (long long)n_layers, (double)tot[0], (double)tot[1], (double)tot[2], (double)tot[3]);
-    }
-    if (err) {
-        char msg[160];
-        snprintf(msg, sizeof msg, "POA graph capacity exceeded (code %d, max_nodes %d): raise max_nodes or cap the reads per consensus", err, Vcap);
-        return fail(ctx, NGSID_EUNSUPPORTED, msg);
-    }
-    return NGSID_OK;
-}
+#include "k5_host.cuh"
 
 // ================================================================================ clustering driver
 namespace {

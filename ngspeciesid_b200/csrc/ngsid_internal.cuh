@@ -63,6 +63,8 @@ struct ngsid_ctx {
     size_t ev_used = 0;
     std::string err;
     int64_t launches = 0;
+    int64_t poa_cells = 0;            // DP cells of the last ngsid_poa_consensus call
+    float poa_ms[3] = {-1.f, -1.f, -1.f};   // last K5 call: kernels + copies, host graph work, whole call
 
     // ---- uploaded reads
     int64_t n_reads = 0, total_bases = 0, total_words = 0;

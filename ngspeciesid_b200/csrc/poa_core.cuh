@@ -6,6 +6,7 @@
 // sites modules/consensus.py:83-92 and :107-126).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define POA_HD __host__ __device__ __forceinline__
@@ -218,69 +219,24 @@ POA_HD int poa_traceback(PoaGraph &G, const int32_t *H, size_t ld, const uint8_t
     return n;
 }
 
-// Order maintenance without a full sort ("path insertion"): a run of new nodes between the old
-// path nodes p and s goes immediately after p (in path order); a run at the start of the path goes
-// immediately before s; a path without old nodes is appended. The alignment is monotone in the
-// current order, so the result is again a topological order (oracle: order_mode 1).
-// path[0..n_path) = nodes of the sequence in path order; scratch: G.score (as int32) and G.stack.
-POA_HD void poa_insert_path_order(PoaGraph &G, int old_V, const int32_t *path, int n_path)
-{
-    int32_t *run_start = reinterpret_cast<int32_t *>(G.score);
-    int32_t *run_len = run_start + G.Vcap;
-    int32_t *new_order = G.stack + n_path;           // path itself lives in G.stack[0..n_path)
-    for (int a = 0; a < old_V; ++a) run_len[a] = 0;
-    int last_old = -1, begin = -1, before_node = -1, before_start = 0, before_len = 0;
-    int tail_start = 0, tail_len = 0;
-    for (int i = 0; i <= n_path; ++i) {
-        const bool is_new = (i < n_path) && (path[i] >= old_V);
-        if (is_new) { if (begin < 0) begin = i; continue; }
-        if (begin >= 0) {
-            const int len = i - begin;
-            if (last_old >= 0) { run_start[last_old] = begin; run_len[last_old] = len; }
-            else if (i < n_path) { before_node = path[i]; before_start = begin; before_len = len; }
-            else { tail_start = begin; tail_len = len; }
-            begin = -1;
-        }
-        if (i < n_path) last_old = path[i];
-    }
-    int n = 0;
-    for (int r = 0; r < old_V; ++r) {
-        const int v = G.order[r];
-        if (v == before_node) for (int t = 0; t < before_len; ++t) new_order[n++] = path[before_start + t];
-        new_order[n++] = v;
-        const int len = run_len[v];
-        if (len) { const int st = run_start[v]; for (int t = 0; t < len; ++t) new_order[n++] = path[st + t]; }
-    }
-    for (int t = 0; t < tail_len; ++t) new_order[n++] = path[tail_start + t];
-    for (int r = 0; r < n; ++r) { const int v = new_order[r]; G.order[r] = v; G.rank[v] = r; }
-}
-
-// Adds a sequence along its alignment (n_aln pairs stored in reverse order in G.aln_*).
-// order_mode 0: spoa's full re-sort; 1: path insertion (see above); 2: leave order/rank to the
-// caller (the wavefront kernel runs poa_topo_sort on shared-memory copies of the edge lists).
-POA_HD void poa_add_alignment(PoaGraph &G, int n_aln, const uint8_t *s, const uint8_t *q, int L, int order_mode = 0)
+// Adds a sequence along its alignment (n_aln pairs stored in reverse order in G.aln_*), then
+// re-sorts (spoa re-sorts after every sequence).
+POA_HD void poa_add_alignment(PoaGraph &G, int n_aln, const uint8_t *s, const uint8_t *q, int L)
 {
     if (L == 0) return;
-    const int old_V = G.V;
-    int32_t *path = G.stack;
-    int n_path = 0;
     int first_pos = -1, last_pos = -1;
     for (int t = n_aln - 1; t >= 0; --t)
         if (G.aln_pos[t] >= 0) { if (first_pos < 0) first_pos = G.aln_pos[t]; last_pos = G.aln_pos[t]; }
     if (first_pos < 0) {
         poa_add_chain(G, s, q, 0, L);
         G.n_seqs++;
-        if (order_mode == 0) poa_topo_sort(G);
-        else if (order_mode == 1) { for (int v = old_V; v < G.V; ++v) path[n_path++] = v; poa_insert_path_order(G, old_V, path, n_path); }
+        poa_topo_sort(G);
         return;
     }
     const int before = G.V;
     poa_add_chain(G, s, q, 0, first_pos);
     int head = (G.V == before) ? -1 : G.V - 1;
-    for (int v = before; v < G.V; ++v) path[n_path++] = v;
-    const int tail_first = G.V;
     const int tail = poa_add_chain(G, s, q, last_pos + 1, L);
-    const int tail_end = G.V;
     int prev_w = head == -1 ? 0 : poa_weight(q, first_pos - 1);
     for (int t = n_aln - 1; t >= 0; --t) {
         const int pos = G.aln_pos[t];
@@ -308,16 +264,26 @@ POA_HD void poa_add_alignment(PoaGraph &G, int n_aln, const uint8_t *s, const ui
             }
         }
         G.cover[node]++;
-        path[n_path++] = node;
         if (head != -1) poa_add_edge(G, head, node, prev_w + poa_weight(q, pos));
         head = node;
         prev_w = poa_weight(q, pos);
     }
     if (tail != -1) poa_add_edge(G, head, tail, prev_w + poa_weight(q, last_pos + 1));
-    for (int v = tail_first; v < tail_end; ++v) path[n_path++] = v;
     G.n_seqs++;
-    if (order_mode == 0) poa_topo_sort(G);
-    else if (order_mode == 1) poa_insert_path_order(G, old_V, path, n_path);
+    poa_topo_sort(G);
+}
+
+// Contents of `src` into the (larger) arrays of `dst`, which has been bound to its own memory.
+inline void poa_graph_copy(PoaGraph &dst, const PoaGraph &src)
+{
+    const size_t V = (size_t)src.V, E = (size_t)src.E, A = (size_t)src.A;
+    dst.V = src.V; dst.E = src.E; dst.A = src.A; dst.n_seqs = src.n_seqs; dst.err = src.err;
+#define POA_CP(field, count) memcpy(dst.field, src.field, (count) * sizeof(*src.field));
+    POA_CP(letter, V) POA_CP(cover, V) POA_CP(in_head, V) POA_CP(in_tail, V) POA_CP(out_head, V) POA_CP(out_tail, V)
+    POA_CP(al_head, V) POA_CP(al_tail, V) POA_CP(order, V) POA_CP(rank, V)
+    POA_CP(e_from, E) POA_CP(e_to, E) POA_CP(e_w, E) POA_CP(e_next_in, E) POA_CP(e_next_out, E)
+    POA_CP(al_node, A) POA_CP(al_next, A)
+#undef POA_CP
 }
 
 POA_HD void poa_relax(PoaGraph &G, int v, bool skip_dead)

@@ -86,8 +86,6 @@ class Engine(object):
         self.offsets = None
         self._q_done = False
         self.rank, self.world = 0, 1
-        self.poa_shape = 0          # K5 kernel shape used when a call does not say (0 wavefront, 1 row)
-        self.poa_order_mode = 0     # row kernel only: 0 spoa's re-sort, 1 path insertion
 
     def close(self):
         if getattr(self, "h", None):
@@ -228,13 +226,10 @@ class Engine(object):
         return (score, nmatch, ncols, win) if want_windows else (score, nmatch, ncols)
 
     def poa_consensus(self, job_off, layer_src, layer_begin, layer_len, aux=None, mode=0, match=5,
-                      mismatch=-4, gap=-2, trim=False, max_nodes=0, shape=None, order_mode=0):
+                      mismatch=-4, gap=-2, trim=False, max_nodes=0):
         """K5: one POA consensus per job. Layers index uploaded reads (>= 0) or aux strings (< 0).
-        shape 0: wavefront kernel, 1: row kernel. order_mode 0: spoa's re-sort after every layer;
-        1 (row kernel only): experimental path insertion.
+        max_nodes > 0 bounds the graph of a job (an error beyond it); 0 = as large as it gets.
         Returns (list of consensus strings, node counts)."""
-        if shape is None:
-            shape, order_mode = self.poa_shape, self.poa_order_mode
         job_off = as_array(job_off, np.int64)
         src, beg, ln = as_array(layer_src, np.int32), as_array(layer_begin, np.int32), as_array(layer_len, np.int32)
         n_jobs = len(job_off) - 1
@@ -249,7 +244,6 @@ class Engine(object):
             n_aux = len(enc)
         p = PoaParams()
         p.mode, p.match, p.mismatch, p.gap, p.trim, p.max_nodes = mode, match, mismatch, gap, 1 if trim else 0, max_nodes
-        p.reserved[0], p.reserved[1] = int(order_mode), int(shape)
         stride = 4 * int(ln.max() if len(ln) else 1) + 64
         out = np.zeros((n_jobs, stride), dtype=np.uint8)
         out_len = np.zeros(n_jobs, dtype=np.int32)
@@ -338,6 +332,10 @@ class Engine(object):
 
     def set_option(self, option, value):
         self._check(self.lib.ngsid_set_option(self.h, option, value))
+
+    def poa_cells(self):
+        """DP cells (graph rows x layer bases, summed) of the last poa_consensus call."""
+        return int(self.lib.ngsid_poa_cells(self.h))
 
     def phase_ms(self, which):
         return float(self.lib.ngsid_phase_ms(self.h, which))

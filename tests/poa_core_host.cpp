@@ -7,7 +7,7 @@
 #include "../ngspeciesid_b200/csrc/poa_core.cuh"
 
 extern "C" int poa_core_host_consensus(const char **seqs, const char **quals, int n, int mode, int m, int x,
-                                       int g, int trim, char *out, int cap, int Vcap, int order_mode)
+                                       int g, int trim, char *out, int cap, int Vcap)
 {
     int Lmax = 1;
     for (int i = 0; i < n; ++i) Lmax = std::max<int>(Lmax, (int)strlen(seqs[i]));
@@ -51,7 +51,7 @@ extern "C" int poa_core_host_consensus(const char **seqs, const char **quals, in
             }
             if (!(mode == 0 && best == 0)) n_aln = poa_traceback(G, H.data(), ld, s, mode, m, x, g, bi, bj);
         }
-        poa_add_alignment(G, n_aln, s, q, L, order_mode);
+        poa_add_alignment(G, n_aln, s, q, L);
         if (G.err) return -100 - G.err;
     }
     int len = poa_consensus(G, trim, (uint8_t *)out, cap - 1);

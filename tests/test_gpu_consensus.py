@@ -21,25 +21,6 @@ def eng():
     e.close()
 
 
-@pytest.fixture(autouse=True, params=["wave", "row"])
-def poa_shape(request, eng):
-    """Every test runs on the wavefront kernel and on the row kernel; both keep spoa's topological
-    re-sort after every layer (oracle order_mode 0)."""
-    from ngspeciesid_b200 import engine as E
-    old = co.ORDER_MODE
-    engines = [eng, E.get_engine(0)]              # the fixture's engine and the one modules/ share
-    shape = 0 if request.param == "wave" else 1
-    co.ORDER_MODE = 0
-    for e in engines:
-        e.poa_shape, e.poa_order_mode = shape, 0
-    try:
-        yield request.param
-    finally:
-        co.ORDER_MODE = old
-        for e in engines:
-            e.poa_shape, e.poa_order_mode = 0, 0
-
-
 def species_reads(n, n_species, seed, lo=700, hi=800):
     from ngspeciesid_b200.synth import simulate_reads
     rs = simulate_reads(n, n_species=n_species, len_lo=lo, len_hi=hi, seed=seed)
@@ -200,18 +181,93 @@ def test_highest_aln_identity(eng):
     assert [c[:2] for c in out] == [[18, 1], [5, 3]] and out[0][3] == ["p1", "p2"]
 
 
-def test_wavefront_falls_back_to_row_kernel(eng, poa_shape, monkeypatch):
-    """A graph that outgrows the wavefront kernel's shared-memory ring must be finished by the row
-    kernel with the same result (the ring is made tiny here)."""
-    if poa_shape != "wave":
-        pytest.skip("fallback only exists for the wavefront shape")
+
+
+def test_all_reads_of_a_large_cluster(eng):
+    """The reference's default --max_seqs_for_consensus -1 (NGSpeciesID:204) feeds EVERY read of a
+    cluster to the POA. 1 000 reads of one strand of one species: the graph grows to several
+    thousand rows (host graphs grow on demand, no max_nodes bound); result = oracle."""
     from ngspeciesid_b200.modules import consensus as C
-    rs, groups, _tpl = species_reads(120, 1, 43, 500, 560)
+    rs, groups, tpl = species_reads(2100, 1, 61, 420, 460)
     recs = [rs.read(i) for i in range(len(rs))]
     eng.upload_records(recs)
-    lst = [i for i in range(len(rs)) if rs.strand[i] == 0][:20]
+    lst = groups[(0, 0)][:1000]
+    assert len(lst) == 1000
+    got, nodes = C.draft_consensus_batch(eng, [lst])
     exp = co.spoa_consensus([recs[i] for i in lst])
-    monkeypatch.setenv("NGSID_K5W_SMEM_KB", "16")
-    got, nodes = C.draft_consensus_batch(eng, [lst, lst[:5]])
-    assert got[0] == exp and got[1] == co.spoa_consensus([recs[i] for i in lst[:5]])
-    assert int(nodes[0]) > 500
+    assert within_tolerance(got[0], exp) and got[0] == exp
+    assert int(nodes[0]) > 3000
+    assert co.edit_distance(got[0], tpl[0]) <= 0.01 * len(tpl[0])
+    assert eng.poa_cells() > 1e9
+    pol = C.polish_batch(eng, got, [lst], 1)[0]
+    assert pol == co.racon_polish(got[0], [recs[i] for i in lst], 1)
+
+
+def test_five_thousand_read_cluster_completes(eng):
+    """a cluster with >= 5 000 reads through the draft and one polishing round with all
+    reads. Too large for the scalar oracle to follow in a test, so the check is against the
+    template (<= 1 % per base) and that a capped graph (max_nodes) is a clean error."""
+    from ngspeciesid_b200 import _lib
+    from ngspeciesid_b200.modules import consensus as C
+    rs, groups, tpl = species_reads(10400, 1, 67, 380, 420)
+    recs = [rs.read(i) for i in range(len(rs))]
+    eng.upload_records(recs)
+    lst = groups[(0, 0)][:5000]
+    assert len(lst) == 5000
+    got, nodes = C.draft_consensus_batch(eng, [lst])
+    assert co.edit_distance(got[0], tpl[0]) <= 0.01 * len(tpl[0])
+    pol = C.polish_batch(eng, got, [lst], 1)[0]
+    assert co.edit_distance(pol, tpl[0]) <= 0.01 * len(tpl[0])
+    with pytest.raises(_lib.NgsidError):
+        C.draft_consensus_batch(eng, [lst[:400]], max_nodes=600)
+    got2, _n = C.draft_consensus_batch(eng, [lst[:20]])            # the context stays usable
+    assert got2[0] == co.spoa_consensus([recs[i] for i in lst[:20]])
+
+
+def test_long_layers_use_the_wide_block(eng):
+    """Layers of 1 500 - 2 000 bases (PacBio configuration): more than 8 column tiles per row."""
+    from ngspeciesid_b200.modules import consensus as C
+    rs, groups, tpl = species_reads(40, 1, 71, 1500, 2000)
+    recs = [rs.read(i) for i in range(len(rs))]
+    eng.upload_records(recs)
+    lst = groups[(0, 0)][:12]
+    got, _n = C.draft_consensus_batch(eng, [lst])
+    assert got[0] == co.spoa_consensus([recs[i] for i in lst])
+
+
+def test_sample_h1_consensus_racon_all_reads(p_table):
+    """BASELINE configs[0]: sample_h1 --ont --consensus --racon with every read of a cluster in the
+    POA (max_seqs_for_consensus -1), through the N-GPU driver on one GPU, against the oracle."""
+    import test_gpu_multi as TM
+    from ngspeciesid_b200 import engine as E
+    from ngspeciesid_b200 import multi_gpu as M
+    from conftest import scenario_reads
+    from oracle import cluster_oracle as oc
+    args = oc.default_args()
+    ra = oc.read_array_from_sorted(oc.sort_stage(scenario_reads("h1"), args.k))
+    p_emp = oc.load_p_emp(p_table, args.k, args.w)
+    engs = [E.Engine(0) for _ in range(4)]
+    try:
+        engs[0].upload_records([(r[3], r[4]) for r in ra])
+        pipe = M.Pipeline(*engs, k=args.k, w=args.w)
+        pipe.cluster(E.max_gap_table(p_emp, 0.1), [r[2] for r in ra], [r[5] for r in ra], 0, len(ra))
+        centers, info = pipe.consensus(0.1, -1, 2)
+    finally:
+        for e in engs:
+            e.close()
+    clusters, reps = oc.single_clustering(list(ra), p_emp, args)
+    import test_multi_gpu_gloo as T
+    by_acc = {r[2]: r for r in ra}
+    drafts, exp = [], []
+    # reference semantics with the oracle, all reads, 2 polishing rounds
+    cents = []
+    for c_id, accs in sorted(clusters.items(), key=lambda x: (len(x[1]), reps[x[0]][5]), reverse=True):
+        if len(accs) >= int(0.1 * len(ra)):
+            recs = [(by_acc[a][3], by_acc[a][4]) for a in accs]
+            cents.append([len(accs), c_id, co.spoa_consensus(recs), recs])
+    assert info["drafts"] == [c[2] for c in cents]
+    assert len(cents) == 2 and len(centers) == 1                     # the two strand clusters merge
+    merged = co.racon_polish(cents[0][2], cents[0][3] + cents[1][3], 2, both_strands=True)
+    assert centers[0][:2] == [cents[0][0] + cents[1][0], cents[0][1]]
+    assert co.edit_distance(centers[0][2], merged) <= TOL * len(merged)
+    assert centers[0][2] == merged
