@@ -55,26 +55,37 @@ struct HostGraph {
 struct Layer { const uint8_t *s; const uint8_t *q; int L; int64_t arena_off; };
 
 // rows of the graph in topological order for the kernel; returns the number of overflow entries
-static int64_t build_rows(const PoaGraph &G, int ring, uint4 *rows, int32_t *ovf, bool count_only, int *max_np)
+static int64_t build_rows(const PoaGraph &G, int ring, uint4 *rows, uint2 *plans, int32_t *ovf, bool count_only, int *max_np)
 {
     int64_t n_ovf = 0;
+    const bool pack16 = G.V + 1 < 65535;
+    const int inl = pack16 ? K5R_INLINE16 : K5R_INLINE32;
     for (int r = 0; r < G.V; ++r) {
         const int v = G.order[r];
         int np = 0;
         for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) ++np;
         if (np > *max_np) *max_np = np;
-        if (count_only) { if (np > 3) n_ovf += np; continue; }
-        uint4 m = make_uint4((uint32_t)G.letter[v] | ((uint32_t)std::min(np, 255) << 8) | (G.out_head[v] < 0 ? K5R_FLAG_SINK : 0u), 0u, 0u, 0u);
+        if (count_only) { if (np > inl) n_ovf += np; continue; }
+        uint32_t f[4] = {(uint32_t)G.letter[v] | ((uint32_t)std::min(np, 255) << 8) | (G.out_head[v] < 0 ? K5R_FLAG_SINK : 0u) |
+                         (pack16 ? K5R_FLAG_PACK16 : 0u), 0u, 0u, 0u};
         int u = 0;
-        if (np > 3) m.y = (uint32_t)n_ovf;
+        if (np > inl) f[1] = (uint32_t)n_ovf;
+        // plan of the row for the pipelined loop: previous row, virtual row, two more near rows
+        uint32_t chain_u = 255, virt_u = np == 0 ? 0u : 255u, npre = 0, generic = np > K5R_MAXE ? 1u : 0u, py = 0;
         for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e], ++u) {
             const int p = G.rank[G.e_from[e]] + 1;
-            if (np > 3) ovf[n_ovf + u] = p;
-            else if (u == 0) m.y = (uint32_t)p; else if (u == 1) m.z = (uint32_t)p; else m.w = (uint32_t)p;
-            if ((r + 1) - p >= ring) rows[p - 1].x |= K5R_FLAG_STORE;        // a far successor reads it from global memory
+            if (np > inl) ovf[n_ovf + u] = p;
+            else if (pack16) f[1 + (u >> 1)] |= (uint32_t)p << ((u & 1) * 16);
+            else f[1 + u] = (uint32_t)p;
+            const int dist = (r + 1) - p;
+            if (dist >= ring) rows[p - 1].x |= K5R_FLAG_STORE;               // a far successor reads it from global memory
+            if (dist == 1) chain_u = (uint32_t)u;
+            else if (dist < ring && npre < 2 && u < 255) { py |= ((uint32_t)dist | ((uint32_t)u << 8)) << (16 * npre); ++npre; }
+            else generic = 1;
         }
-        if (np > 3) n_ovf += np;
-        rows[r] = m;
+        if (np > inl) n_ovf += np;
+        rows[r] = make_uint4(f[0], f[1], f[2], f[3]);
+        plans[r] = make_uint2(chain_u | (virt_u << 8) | (npre << 16) | (generic << 24), py);
     }
     return n_ovf;
 }
@@ -175,6 +186,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     CUDA_TRY(ctx, ctx->d_poa_err.ensure(64));
     const int max_nodes = params->max_nodes;
     int64_t total_cells = 0;
+    long long dbg[5] = {0, 0, 0, 0, 0}, dbg_dp = 0, dbg_tb = 0, dbg_wait = 0, ph[4] = {0, 0, 0, 0};
 
     for (int64_t step = 0; step < max_job_layers; ++step) {
         // ---- layers that need no DP (first layer of a job, empty layers) go straight into the graph
@@ -200,7 +212,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
 #pragma omp parallel for num_threads(T) schedule(dynamic, 1)
         for (int x = 0; x < nd; ++x) {
             const int j = dp_jobs[x];
-            n_ovf_of[j] = build_rows(graphs[j].G, ring, nullptr, nullptr, true, &np_max[x]);
+            n_ovf_of[j] = build_rows(graphs[j].G, ring, nullptr, nullptr, nullptr, true, &np_max[x]);
         }
         desc.assign((size_t)nd, K5RJob());
         int64_t meta_n = 0, ovf_n = 0, mat_n = 0, path_n = 0;
@@ -232,30 +244,33 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         const size_t b_desc = ((size_t)nd * sizeof(K5RJob) + 255) & ~(size_t)255;
         const size_t b_meta = ((size_t)meta_n * 16 + 255) & ~(size_t)255;
         const size_t b_ovf = ((size_t)ovf_n * 4 + 255) & ~(size_t)255;
-        CUDA_TRY(ctx, pin_meta.ensure(b_desc + b_meta + b_ovf));
+        const size_t b_plan = ((size_t)meta_n * 8 + 255) & ~(size_t)255;
+        CUDA_TRY(ctx, pin_meta.ensure(b_desc + b_meta + b_ovf + b_plan));
         uint8_t *hm = pin_meta.as<uint8_t>();
         memcpy(hm, desc.data(), (size_t)nd * sizeof(K5RJob));
         uint4 *h_rows = reinterpret_cast<uint4 *>(hm + b_desc);
         int32_t *h_ovf = reinterpret_cast<int32_t *>(hm + b_desc + b_meta);
+        uint2 *h_plan = reinterpret_cast<uint2 *>(hm + b_desc + b_meta + b_ovf);
 #pragma omp parallel for num_threads(T) schedule(dynamic, 1)
         for (int x = 0; x < nd; ++x) {
             int dummy = 0;
-            build_rows(graphs[dp_jobs[x]].G, ring, h_rows + desc[x].meta_off, h_ovf + desc[x].ovf_off, false, &dummy);
+            build_rows(graphs[dp_jobs[x]].G, ring, h_rows + desc[x].meta_off, h_plan + desc[x].meta_off, h_ovf + desc[x].ovf_off, false, &dummy);
         }
         ms_host += since(t_h);
         auto t_d = std::chrono::steady_clock::now();
-        CUDA_TRY(ctx, ctx->d_poa_meta.ensure(b_desc + b_meta + b_ovf));
+        CUDA_TRY(ctx, ctx->d_poa_meta.ensure(b_desc + b_meta + b_ovf + b_plan));
         CUDA_TRY(ctx, ctx->d_poa_h.ensure((size_t)mat_n * 4 + 256));
         CUDA_TRY(ctx, ctx->d_poa_dir.ensure((size_t)mat_n + 256));
-        CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)path_n * 8 + (size_t)nd * 16 + 256));
-        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_poa_meta.p, hm, b_desc + b_meta + b_ovf, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, ctx->d_poa_out.ensure((size_t)path_n * 8 + (size_t)nd * 64 + 256));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_poa_meta.p, hm, b_desc + b_meta + b_ovf + b_plan, cudaMemcpyHostToDevice, ctx->stream));
         int32_t *d_out = reinterpret_cast<int32_t *>(ctx->d_poa_out.as<uint8_t>() + (size_t)path_n * 8);
-        CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, (size_t)nd * 16, ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(d_out, 0, (size_t)nd * 64, ctx->stream));
         K5RArgs A;
         A.jobs = ctx->d_poa_meta.as<K5RJob>();
         A.layers = d_lseq;
         A.meta = reinterpret_cast<const uint4 *>(ctx->d_poa_meta.as<uint8_t>() + b_desc);
         A.ovf = reinterpret_cast<const int32_t *>(ctx->d_poa_meta.as<uint8_t>() + b_desc + b_meta);
+        A.plan = reinterpret_cast<const uint2 *>(ctx->d_poa_meta.as<uint8_t>() + b_desc + b_meta + b_ovf);
         A.H = ctx->d_poa_h.as<int32_t>(); A.DIR = ctx->d_poa_dir.as<uint8_t>();
         A.path = ctx->d_poa_out.as<int2>(); A.out = d_out; A.ld = ld; A.ring = ring;
         const size_t smem = k5r_smem_bytes(NW, ring);
@@ -268,21 +283,27 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         else { if (NW <= 8) K5R_LAUNCH(0, 256); else K5R_LAUNCH(0, 1024); }
 #undef K5R_LAUNCH
         KERNEL_CHECK(ctx);
-        CUDA_TRY(ctx, pin_path.ensure((size_t)path_n * 8 + (size_t)nd * 16));
-        CUDA_TRY(ctx, cudaMemcpyAsync(pin_path.p, ctx->d_poa_out.p, (size_t)path_n * 8 + (size_t)nd * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, pin_path.ensure((size_t)path_n * 8 + (size_t)nd * 64));
+        CUDA_TRY(ctx, cudaMemcpyAsync(pin_path.p, ctx->d_poa_out.p, (size_t)path_n * 8 + (size_t)nd * 64, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         ms_dev += since(t_d);
         t_h = std::chrono::steady_clock::now();
         const int2 *h_path = pin_path.as<int2>();
         const int32_t *h_out = reinterpret_cast<const int32_t *>(pin_path.as<uint8_t>() + (size_t)path_n * 8);
+        for (int x = 0; x < nd; ++x) {
+            dbg[0] = std::max<long long>(dbg[0], h_out[x * 16 + 3]); dbg[1] = std::max<long long>(dbg[1], h_out[x * 16 + 4]);
+            dbg[2] += h_out[x * 16 + 5]; dbg[3] += desc[x].V; dbg[4] = std::max<long long>(dbg[4], h_out[x * 16 + 6]);
+            for (int q = 0; q < 4; ++q) ph[q] += h_out[x * 16 + 8 + q];
+        }
+        dbg_dp += dbg[0]; dbg_tb += dbg[1]; dbg_wait += dbg[4]; dbg[0] = dbg[1] = dbg[4] = 0;
         // ---- graph update + re-sort on host threads
 #pragma omp parallel for num_threads(T) schedule(dynamic, 1)
         for (int x = 0; x < nd; ++x) {
             const int j = dp_jobs[x];
             const int64_t l = job_off[j] + step;
             PoaGraph &G = graphs[j].G;
-            if (h_out[x * 4 + 2]) { jerr[j] = h_out[x * 4 + 2]; continue; }
-            const int n = h_out[x * 4];
+            if (h_out[x * 16 + 2]) { jerr[j] = h_out[x * 16 + 2]; continue; }
+            const int n = h_out[x * 16];
             const int2 *pp = h_path + desc[x].path_off;
             for (int t = 0; t < n; ++t) {
                 G.aln_node[t] = pp[t].x > 0 ? G.order[pp[t].x - 1] : -1;
@@ -310,6 +331,16 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
     for (int64_t j = 0; j < n_jobs; ++j) worst = std::max(worst, jerr[j]);
     ctx->poa_cells = total_cells;
     ctx->poa_ms[0] = (float)ms_dev; ctx->poa_ms[1] = (float)ms_host; ctx->poa_ms[2] = (float)since(t_call);
+    if (getenv("NGSID_POA_TIMING"))
+        fprintf(stderr, "[k5] jobs %lld layers %lld steps %lld threads %d: device+copies %.1f ms, host graphs %.1f ms, call %.1f ms, %.3g cells\n",
+                (long long)n_jobs, (long long)n_layers, (long long)max_job_layers, T, ms_dev, ms_host, ctx->poa_ms[2], (double)total_cells);
+    if (getenv("NGSID_POA_TIMING"))
+        fprintf(stderr, "[k5]   slowest job per step, summed: DP %.1f Mcycles, traceback %.1f Mcycles, warp 1 waiting %.1f Mcycles; rows %lld, far-predecessor loads %lld\n",
+                dbg_dp * 1024e-6, dbg_tb * 1024e-6, dbg_wait * 1024e-6, dbg[3], dbg[2]);
+    if (getenv("NGSID_POA_TIMING"))
+        fprintf(stderr, "[k5]   warp 1, all jobs: cycles per row in back-pressure %.0f, predecessors %.0f, scan %.0f, stores %.0f\n",
+                ph[0] * 1024.0 / std::max<long long>(1, dbg[3]), ph[1] * 1024.0 / std::max<long long>(1, dbg[3]),
+                ph[2] * 1024.0 / std::max<long long>(1, dbg[3]), ph[3] * 1024.0 / std::max<long long>(1, dbg[3]));
     if (worst) {
         char msg[160];
         snprintf(msg, sizeof msg, "POA failed (code %d: 1-3 graph capacity, 5 output buffer, 7 in-edges, 8 no end cell)", worst);
