@@ -8,12 +8,12 @@ bench.py -- reads/s clustered + consensus bp/s on synthetic 750 bp ONT amplicon 
     python bench.py --impl reference ...       # the unmodified reference on the host cores
 
 Workloads (config.workload names the one that ran):
-  N = 1, 2, 4 : BASELINE.json configs[1] per GPU: 100 k reads, 10 species, k=13 w=20 (weak scaling:
+  every N     : BASELINE.json configs[1] per GPU: 100 k reads, 10 species, k=13 w=20 (weak scaling:
                 N x 100 k reads, `--t N` semantics of modules/parallelize.py);
                 the consensus leg is configs[2] (cluster + POA consensus + 3 racon-style rounds).
-  N = 8       : BASELINE.json configs[3]: 10^6 reads, 50 species, cluster + consensus with
-                --abundance_ratio 0.005, NCCL exchange of representatives and of cluster reads.
-  --config c1 / c3 forces one of them at any N (reads per GPU: 100 k / 125 k).
+  N = 8 also  : `north_star_configs3` = BASELINE.json configs[3] end to end: 10^6 reads, 50 species,
+                cluster + consensus with --abundance_ratio 0.005 (the same JSON shape, nested).
+  --config c1 / c3 forces one of them as the main line at any N (reads per GPU: 100 k / 125 k).
 
 One "step" = one pass of the clustering hot path over the whole batch of every rank: K1 minimizers
 + K0 quality statistics + the greedy pass (K2/K3 mapping, K4 block alignment) and, for N > 1, the
@@ -214,7 +214,7 @@ class ClockSampler(object):
 
 # ------------------------------------------------------------------------------------ GPU arm
 def pick_config(args, world):
-    name = args.config if args.config != "auto" else ("c3" if world >= 8 else "c1")
+    name = args.config if args.config != "auto" else "c1"
     cfg = dict(CONFIGS[name])
     if args.reads:
         cfg["reads_per_gpu"] = args.reads
@@ -241,7 +241,45 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    p_emp = p_minimizers_shared.p_emp_for(K, W)
+    max_gap = E.max_gap_table(p_emp, 0.1)
+    eng, mg, ce, pe = E.Engine(local), E.Engine(local), E.Engine(local), E.Engine(local)
+    if world > 1:
+        # the library's own communicator (NCCL inside libngsid.so); the id travels over torch.distributed
+        uid = [E.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.nccl_init(uid[0], rank, world)
+        for e in (mg, ce, pe):
+            e.nccl_share(eng)
+    env = dict(torch=torch, dist=dist, E=E, M=M, rank=rank, world=world, local=local, p_emp=p_emp, max_gap=max_gap,
+               engines=(eng, mg, ce, pe))
     cfg = pick_config(args, world)
+    result = _measure(args, cfg, env)
+    if world >= 8 and args.config == "auto" and not args.no_north_star:
+        # the north-star run itself: BASELINE.json configs[3], cluster + consensus end to end on the same ranks
+        import copy
+        a3 = copy.copy(args)
+        a3.config, a3.steps, a3.warmup = "c3", max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
+        a3.no_roofline = a3.no_cpu = a3.no_modules = True
+        a3.reads = 0
+        r3 = _measure(a3, pick_config(a3, world), env)
+        if rank == 0:
+            result["north_star_configs3"] = r3
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        for e in (pe, ce, mg, eng):
+            e.close()
+        dist.destroy_process_group()
+
+
+def _measure(args, cfg, env):
+    """One workload on the ranks of `env`: clustering (resident + end to end), consensus of the final
+    clusters, and on rank 0 the optional single-GPU legs. Returns the result dict on rank 0."""
+    torch, dist, E, M = env["torch"], env["dist"], env["E"], env["M"]
+    rank, world, local, p_emp, max_gap = env["rank"], env["world"], env["local"], env["p_emp"], env["max_gap"]
+    eng, mg, ce, pe = env["engines"]
     n_total = cfg["reads_per_gpu"] * world
     seed = args.seed + world - 1
     if world > 1:
@@ -250,8 +288,6 @@ def run_ours(args):
             make_workload(n_total, seed, n_species=cfg["species"])
         dist.barrier()
     seq, qual, offsets, acc, templates = make_workload(n_total, seed, n_species=cfg["species"], with_templates=True)
-    p_emp = p_minimizers_shared.p_emp_for(K, W)
-    max_gap = E.max_gap_table(p_emp, 0.1)
 
     # --t N semantics: N consecutive batches of the score-sorted list by cumulative nucleotides
     bounds = batch_bounds(np.diff(offsets), world)
@@ -264,14 +300,6 @@ def run_ours(args):
     my_scores = [float(a.split("_")[-1]) for a in my_acc]
     del seq, qual                                     # every rank keeps its own batch only
 
-    eng, mg, ce, pe = E.Engine(local), E.Engine(local), E.Engine(local), E.Engine(local)
-    if world > 1:
-        # the library's own communicator (NCCL inside libngsid.so); the id travels over torch.distributed
-        uid = [E.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.nccl_init(uid[0], rank, world)
-        for e in (mg, ce, pe):
-            e.nccl_share(eng)
     pipe = M.Pipeline(eng, mg, ce, pe, rank=rank, world=world, k=K, w=W)
 
     def barrier():
@@ -472,13 +500,7 @@ def run_ours(args):
         oc.single_clustering(ra, p_emp, oc.default_args(), stats)
         exp = [w_ for _r, w_, _h in stats.trace]
         result["parity_sample_identical"] = bool([int(x) for x in pipe.local_assign[:ns]] == exp)
-    if rank == 0:
-        print(json.dumps(result))
-    if world > 1:
-        dist.barrier()
-        for e in (pe, ce, mg, eng):
-            e.close()
-        dist.destroy_process_group()
+    return result
 
 
 def workload_config(cfg, world):
@@ -600,6 +622,7 @@ def main():
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--no-consensus", dest="no_consensus", action="store_true")
     ap.add_argument("--no-modules", dest="no_modules", action="store_true")
+    ap.add_argument("--no-north-star", dest="no_north_star", action="store_true", help="N = 8: skip the configs[3] run")
     ap.add_argument("--abundance-ratio", dest="abundance_ratio", type=float, default=None)
     ap.add_argument("--max-seqs", dest="max_seqs", type=int, default=None, help="--max_seqs_for_consensus of the consensus leg")
     ap.add_argument("--racon-iter", dest="racon_iter", type=int, default=None)

@@ -82,55 +82,64 @@ def find_locations(query, target, k):
 
 
 def read_barcodes(primer_file):
-    """Reference: modules/barcode_trimmer.py:15-23."""
-    barcodes = {acc + "_fw": seq.strip() for acc, (seq, _) in help_functions.readfq(open(primer_file, "r"))}
-    for acc, seq in list(barcodes.items()):
-        barcodes[acc[:-3] + "_rc"] = reverse_complement(seq.upper())
-    return barcodes
+    """Primers of a FASTA file as {name_fw: sequence, name_rc: reverse complement (upper case)}, the
+    forward entries first (behaviour of the reference's modules/barcode_trimmer.py:15-23)."""
+    with open(primer_file, "r") as handle:
+        forward = [(name, seq.strip()) for name, (seq, _qual) in help_functions.readfq(handle)]
+    table = dict((name + "_fw", seq) for name, seq in forward)
+    table.update((name + "_rc", reverse_complement(seq.upper())) for name, seq in forward)
+    return table
+
+
+_UNIVERSAL_TAILS = (("1_F", "TTTCTGTTGGTGCTGATATTGC", "fw"), ("2_R", "ACTTGCCTGTCGCTCTATCTTC", "rc"))
 
 
 def get_universal_tails():
-    """Reference: modules/barcode_trimmer.py:25-31."""
-    barcodes = {"1_F_fw": "TTTCTGTTGGTGCTGATATTGC", "2_R_rc": "ACTTGCCTGTCGCTCTATCTTC"}
-    barcodes["1_F_rc"] = reverse_complement(barcodes["1_F_fw"])
-    barcodes["2_R_fw"] = reverse_complement(barcodes["2_R_rc"])
-    return barcodes
+    """The two ONT universal tails in both orientations (reference: modules/barcode_trimmer.py:25-31;
+    the second tail is given as its reverse complement there too)."""
+    table = {"%s_%s" % (name, strand): seq for name, seq, strand in _UNIVERSAL_TAILS}
+    for name, seq, strand in _UNIVERSAL_TAILS:
+        table["%s_%s" % (name, "rc" if strand == "fw" else "fw")] = reverse_complement(seq)
+    return table
 
 
 def find_barcode_locations(center, barcodes, primer_max_ed):
     """Reference: modules/barcode_trimmer.py:34-59 -> [(primer name, start, end, distance)] with
     the first location of every primer that is found."""
-    all_locations = []
-    for primer_acc, primer_seq in barcodes.items():
-        ed, locations = find_locations(primer_seq, center, primer_max_ed)
-        logging.debug(f"{locations} {ed}")
-        if locations:
-            all_locations.append((primer_acc, locations[0][0], locations[0][1], ed))
-    return all_locations
+    hits = []
+    for name, primer in barcodes.items():
+        distance, where = find_locations(primer, center, primer_max_ed)
+        logging.debug(f"{where} {distance}")
+        if where:
+            first_start, first_end = where[0]
+            hits.append((name, first_start, first_end, distance))
+    return hits
+
+
+def _trimmed_span(center, barcodes, window, max_ed):
+    """[a, b) of `center` that survives: behind the furthest end index of a primer hit inside the
+    first `window` bases, in front of the earliest primer hit inside the last `window` bases."""
+    head_hits = find_barcode_locations(center[:window], barcodes, max_ed)
+    tail_hits = find_barcode_locations(center[-window:], barcodes, max_ed)
+    a = max([0] + [end for _n, _s, end, _d in head_hits])
+    b = len(center)
+    if tail_hits:
+        first = min([len(center)] + [start for _n, start, _e, _d in tail_hits])
+        b = len(center) - (window - first)
+    return a, b
 
 
 def remove_barcodes(centers, barcodes, args):
-    """Reference: modules/barcode_trimmer.py:62-104: cuts every consensus in `centers`
-    ([n_reads, c_id, sequence, reads_path]) behind the last primer hit of its first `trim_window`
-    bases and in front of the earliest hit of its last `trim_window` bases; returns whether any
-    sequence changed. Like the reference, a hit at the beginning cuts at its (inclusive) end index."""
-    centers_updated = False
-    for i, (_nr_reads, _c_id, center, _reads_path) in enumerate(centers):
-        trim_window = len(center) // 2 if 2 * args.trim_window > len(center) else args.trim_window
-        begin = find_barcode_locations(center[:trim_window], barcodes, args.primer_max_ed)
-        end = find_barcode_locations(center[-trim_window:], barcodes, args.primer_max_ed)
-        cut_start = 0
-        for _bc, _start, stop, _ed in begin:
-            if stop > cut_start:
-                cut_start = stop
-        cut_end = len(center)
-        if end:
-            earliest_hit = len(center)
-            for _bc, start, _stop, _ed in end:
-                if start < earliest_hit:
-                    earliest_hit = start
-            cut_end = len(center) - (trim_window - earliest_hit)
-        if cut_start > 0 or cut_end < len(center):
-            centers[i][2] = center[cut_start:cut_end]
-            centers_updated = True
-    return centers_updated
+    """Trims the primers off every consensus of `centers` ([n_reads, c_id, sequence, reads_path]) in
+    place and tells whether anything changed (reference: modules/barcode_trimmer.py:62-104, including
+    its conventions: the search window shrinks to half the sequence for short consensi, and a hit at
+    the beginning cuts at the hit's inclusive end index)."""
+    changed = False
+    for entry in centers:
+        center = entry[2]
+        window = args.trim_window if 2 * args.trim_window <= len(center) else len(center) // 2
+        a, b = _trimmed_span(center, barcodes, window, args.primer_max_ed)
+        if a > 0 or b < len(center):
+            entry[2] = center[a:b]
+            changed = True
+    return changed

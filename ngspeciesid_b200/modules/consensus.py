@@ -224,45 +224,52 @@ def run_medaka(reads_to_center, center_file, outfolder, cores, medaka_model, out
         subprocess.check_call(cmd, stdout=out, stderr=err)
 
 
+def _pair_identities(eng, firsts, seconds):
+    """highest_aln_identity for many pairs in ONE K4 launch: identity (equal columns / all columns of
+    the semi-global alignment, gap open 3 / extend 1) of firsts[i] against seconds[i] and against its
+    reverse complement; the larger of the two."""
+    n = len(firsts)
+    if n == 0:
+        return np.zeros(0)
+    if eng.n_reads == 0:
+        eng.upload_records([("ACGT", "5555")])
+    aux = list(firsts) + list(seconds) + [reverse_complement(x) for x in seconds]
+    a = np.concatenate([-(np.arange(n) + 1), -(np.arange(n) + 1)]).astype(np.int32)
+    b = np.concatenate([-(np.arange(n) + n + 1), -(np.arange(n) + 2 * n + 1)]).astype(np.int32)
+    _score, match, cols = eng.sg_align_paths(a, b, np.full(2 * n, 3, dtype=np.int32), aux=aux)
+    ident = match / np.maximum(cols, 1).astype(np.float64)
+    return ident[:n], ident[n:]
+
+
 def highest_aln_identity(seq, seq2):
     """Reference: modules/consensus.py:129-145: identity (equal columns / all columns) of the
     semi-global alignment (open 3, extend 1) in the better of the two orientations."""
-    eng = _engine.get_engine()
-    if eng.n_reads == 0:
-        eng.upload_records([("ACGT", "5555")])
-    _s, m, c = eng.sg_align_paths([-1, -1], [-2, -3], [3, 3], aux=[seq, reverse_complement(seq2), seq2])
-    ident_rc = m[0] / float(c[0])
-    ident_fw = m[1] / float(c[1])
-    logging.debug("Rec comp orientation identity %: {0}".format(ident_rc))
-    logging.debug("Forward orientation identity %: {0}".format(ident_fw))
-    return max([ident_fw, ident_rc])
+    fw, rc = _pair_identities(_engine.get_engine(), [seq], [seq2])
+    logging.debug("Rec comp orientation identity %: {0}".format(rc[0]))
+    logging.debug("Forward orientation identity %: {0}".format(fw[0]))
+    return max([float(fw[0]), float(rc[0])])
 
 
 def detect_reverse_complements(centers, rc_identity_threshold):
-    """Reference: modules/consensus.py:148-183, including its bookkeeping quirks (the inner loop does
-    not skip centres that were already merged, and re-binds `reads_path`)."""
-    filtered_centers = []
-    already_removed = set()
-    for i, (nr_reads_in_cl, c_id, seq, reads_path) in enumerate(centers):
-        all_reads = [reads_path] if type(reads_path) != list else reads_path
-        merged_nr_reads = nr_reads_in_cl
-        if c_id in already_removed:
-            continue
-        elif i == len(centers) - 1:
-            filtered_centers.append([merged_nr_reads, c_id, seq, all_reads])
-        else:
-            for j, (nr_reads_in_cl2, c_id2, seq2, reads_path) in enumerate(centers[i + 1:]):
-                if highest_aln_identity(seq, seq2) >= rc_identity_threshold:
-                    merged_nr_reads += nr_reads_in_cl2
-                    already_removed.add(c_id2)
-                    if type(reads_path) != list:
-                        all_reads.append(reads_path)
-                    else:
-                        for rp in reads_path:
-                            all_reads.append(rp)
-            filtered_centers.append([merged_nr_reads, c_id, seq, all_reads])
-    logging.debug("{0} consensus formed.".format(len(filtered_centers)))
-    return filtered_centers
+    """Merges centres that are (reverse-complement) copies of an earlier, larger centre; behaviour of
+    the reference's modules/consensus.py:148-183: a centre that has not been absorbed looks at EVERY
+    later centre (also at ones an earlier centre absorbed already) and absorbs those whose identity
+    reaches the threshold; the result rows are [merged read count, c_id, sequence, [read files]].
+    All pair identities come from one alignment launch instead of one call per pair."""
+    from ..multi_gpu import merge_reverse_complements
+    n = len(centers)
+    pairs = [(i, j) for i in range(n) for j in range(i + 1, n)]
+    ident = np.zeros((n, n))
+    if pairs:
+        fw, rc = _pair_identities(_engine.get_engine(), [centers[i][2] for i, _j in pairs], [centers[j][2] for _i, j in pairs])
+        for (i, j), x, y in zip(pairs, fw, rc):
+            ident[i, j] = max(x, y)
+    files = [list(c[3]) if isinstance(c[3], list) else [c[3]] for c in centers]
+    merged = []
+    for i, total, members in merge_reverse_complements([c[0] for c in centers], ident, rc_identity_threshold):
+        merged.append([total, centers[i][1], centers[i][2], [f for m in members for f in files[m]]])
+    logging.debug("{0} consensus formed.".format(len(merged)))
+    return merged
 
 
 def form_draft_consensus(clusters, representatives, sorted_reads_fastq_file, work_dir, abundance_cutoff, args):
@@ -307,45 +314,61 @@ def form_draft_consensus(clusters, representatives, sorted_reads_fastq_file, wor
     return centers
 
 
-def polish_sequences(centers, args):
-    """Reference: modules/consensus.py:186-246: same files (consensus_reference_<id>.fasta,
-    reads_to_consensus_<id>.fastq, racon_cl_id_<id>/ or medaka_cl_id_<id>/) and the same update of
-    centers[i][2]. With --racon all centres are polished in one batch (the centres are
-    independent); --medaka shells out per centre like the reference."""
-    medaka = bool(getattr(args, "medaka", False))
-    prefix = "medaka_cl_id_" if medaka else "racon_cl_id_"
-    for folder in glob.glob(os.path.join(args.outfolder, prefix + "*")):
+def _clear_previous_outputs(outfolder, prefix):
+    for folder in glob.glob(os.path.join(outfolder, prefix + "*")):
         shutil.rmtree(folder)
-    for file in glob.glob(os.path.join(args.outfolder, "consensus_reference_*")):
-        os.remove(file)
-    jobs = []
-    for i, (nr_reads_in_cluster, c_id, center, all_reads) in enumerate(centers):
-        spoa_center_file = os.path.join(args.outfolder, "consensus_reference_{0}.fasta".format(c_id))
-        with open(spoa_center_file, "w") as f:
-            f.write(">{0}\n{1}\n".format("consensus_cl_id_{0}_total_supporting_reads_{1}".format(c_id, nr_reads_in_cluster), center))
-        all_reads_file = os.path.join(args.outfolder, "reads_to_consensus_{0}.fastq".format(c_id))
-        with open(all_reads_file, "w") as f:
-            for fasta_file in all_reads:
-                reads = {acc: (seq, qual) for acc, seq, qual in _read_fastq(fasta_file)}
-                for acc, (seq, qual) in reads.items():
-                    f.write("@{0}\n{1}\n{2}\n{3}\n".format(acc.split()[0], seq, "+", qual))
-        polishing_outfolder = os.path.join(args.outfolder, "{0}{1}".format(prefix, c_id))
-        if medaka:
-            help_functions.mkdir_p(polishing_outfolder)
-            run_medaka(all_reads_file, spoa_center_file, polishing_outfolder, "1", args.medaka_model,
-                       outfastq=getattr(args, "medaka_fastq", False))
-            for name in ("consensus.fasta", "consensus.fastq"):
-                if os.path.isfile(os.path.join(polishing_outfolder, name)):
-                    with open(os.path.join(polishing_outfolder, name), "r") as cf:
-                        centers[i][2] = cf.readlines()[1].strip()
-                    break
-            assert centers[i][2], "Medaka consensus sequence not found"
+    for stale in glob.glob(os.path.join(outfolder, "consensus_reference_*")):
+        os.remove(stale)
+
+
+def _write_centre_inputs(outfolder, c_id, n_reads, centre, read_files):
+    """consensus_reference_<c_id>.fasta and reads_to_consensus_<c_id>.fastq of one centre
+    (modules/consensus.py:201-215 of the reference: one record per accession and file, the accession
+    cut at its first blank). Returns both paths."""
+    fasta = os.path.join(outfolder, "consensus_reference_{0}.fasta".format(c_id))
+    with open(fasta, "w") as f:
+        f.write(">consensus_cl_id_{0}_total_supporting_reads_{1}\n{2}\n".format(c_id, n_reads, centre))
+    fastq = os.path.join(outfolder, "reads_to_consensus_{0}.fastq".format(c_id))
+    with open(fastq, "w") as f:
+        for path in read_files:
+            unique = {}
+            for acc, seq, qual in _read_fastq(path):
+                unique[acc] = (seq, qual)
+            f.writelines("@{0}\n{1}\n+\n{2}\n".format(acc.split()[0], seq, qual) for acc, (seq, qual) in unique.items())
+    return fasta, fastq
+
+
+def _second_line(path):
+    with open(path, "r") as f:
+        return f.readlines()[1].strip()
+
+
+def polish_sequences(centers, args):
+    """Polishes every centre in place (centers[i][2]) and returns `centers`; files and folders as the
+    reference writes them (modules/consensus.py:186-246): consensus_reference_<id>.fasta,
+    reads_to_consensus_<id>.fastq, racon_cl_id_<id>/ or medaka_cl_id_<id>/ with consensus.fasta.
+    With --racon all centres go through the kernels in one batch (they are independent); --medaka
+    shells out per centre like the reference."""
+    use_medaka = bool(getattr(args, "medaka", False))
+    prefix = "medaka_cl_id_" if use_medaka else "racon_cl_id_"
+    _clear_previous_outputs(args.outfolder, prefix)
+    racon_jobs = []
+    for row in centers:
+        n_reads, c_id, centre, read_files = row
+        fasta, fastq = _write_centre_inputs(args.outfolder, c_id, n_reads, centre, read_files)
+        folder = os.path.join(args.outfolder, prefix + str(c_id))
+        if use_medaka:
+            help_functions.mkdir_p(folder)
+            run_medaka(fastq, fasta, folder, "1", args.medaka_model, outfastq=getattr(args, "medaka_fastq", False))
+            produced = [p for p in (os.path.join(folder, "consensus.fasta"), os.path.join(folder, "consensus.fastq")) if os.path.isfile(p)]
+            if produced:
+                row[2] = _second_line(produced[0])
+            assert row[2], "Medaka consensus sequence not found"
         elif args.racon:
-            help_functions.mkdir_p(polishing_outfolder)
-            jobs.append((all_reads_file, spoa_center_file, polishing_outfolder, i))
-    if jobs:
-        _racon_batch([j[:3] for j in jobs], args.racon_iter)
-        for _r, _c, polishing_outfolder, i in jobs:
-            with open(os.path.join(polishing_outfolder, "consensus.fasta"), "r") as cf:
-                centers[i][2] = cf.readlines()[1].strip()
+            help_functions.mkdir_p(folder)
+            racon_jobs.append((fastq, fasta, folder, row))
+    if racon_jobs:
+        _racon_batch([job[:3] for job in racon_jobs], args.racon_iter)
+        for _fq, _fa, folder, row in racon_jobs:
+            row[2] = _second_line(os.path.join(folder, "consensus.fasta"))
     return centers

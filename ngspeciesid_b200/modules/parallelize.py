@@ -46,21 +46,22 @@ def batch_list(lst, nr_cores=1, batch_type="nr_reads", merge_consecutive=False):
 
 
 def print_intermediate_results(clusters, cluster_seq_origin, args, iter_nr):
-    """Reference: modules/parallelize.py:83-104: the snapshot of a merge round,
-    <outfolder>/<iter_nr>/pre_clusters.csv (cluster id, read name without its score suffix; clusters
-    by size descending, members in list order) and cluster_origins.csv (one line per
-    representative). Nothing reads these files back, in the reference or here."""
-    path = args.outfolder + "/{0}".format(iter_nr)
-    help_functions.mkdir_p(path)
-    ordered = sorted(clusters.items(), key=lambda x: len(x[1]), reverse=True)
-    with open(os.path.join(path, "pre_clusters.csv"), "w") as f:
-        for c_id, accs in ordered:
-            for r_acc in accs:
-                f.write("{0}\t{1}\n".format(c_id, "_".join(r_acc.split("_")[:-1])))
-    with open(os.path.join(path, "cluster_origins.csv"), "w") as f:
-        for c_id, _accs in ordered:
-            read_cl_id, _b, acc, seq, qual, score, error_rate, _comp = cluster_seq_origin[c_id]
-            f.write("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\n".format(read_cl_id, acc, seq, qual, score, error_rate))
+    """Snapshot of a merge round as the reference leaves it (modules/parallelize.py:83-104):
+    <outfolder>/<iter_nr>/pre_clusters.csv -- cluster id and read name (score suffix cut off), clusters
+    largest first, members in list order -- and cluster_origins.csv, one line per representative.
+    Nothing reads these files back, in the reference or here."""
+    folder = "{0}/{1}".format(args.outfolder, iter_nr)
+    help_functions.mkdir_p(folder)
+    by_size = sorted(clusters, key=lambda c: len(clusters[c]), reverse=True)
+    member_lines, origin_lines = [], []
+    for c_id in by_size:
+        member_lines.extend("{0}\t{1}\n".format(c_id, acc.rsplit("_", 1)[0] if "_" in acc else "") for acc in clusters[c_id])
+        rid, _batch, acc, seq, qual, score, err, _comp = cluster_seq_origin[c_id]
+        origin_lines.append("{0}\t{1}\t{2}\t{3}\t{4}\t{5}\n".format(rid, acc, seq, qual, score, err))
+    with open(os.path.join(folder, "pre_clusters.csv"), "w") as f:
+        f.writelines(member_lines)
+    with open(os.path.join(folder, "cluster_origins.csv"), "w") as f:
+        f.writelines(origin_lines)
 
 
 def _snapshot(all_cl, all_rp, args, it):
@@ -121,6 +122,8 @@ def parallel_clustering_ranks(read_array, p_emp_probs, args, group=None, cluster
     import torch.distributed as dist
     fn = cluster_fn if cluster_fn is not None else cluster.reads_to_clusters
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if cluster_fn is None and getattr(args, "device", None) is None:
+        args.device = int(os.environ.get("LOCAL_RANK", "0"))        # one GPU per rank
     batches = list(batch_list(read_array, args.nr_cores, batch_type=args.batch_type))
     num = args.nr_cores
     cl = [{r[0]: [r[2]] for r in b} for b in batches]
