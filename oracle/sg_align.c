@@ -45,6 +45,17 @@
 
 enum { T_DIAG = 1, T_D = 2, T_I = 4, T_D_OPEN = 8, T_I_OPEN = 16 };
 
+/*
+ * Tie-break variants for the sensitivity study (tests/test_aligner_pinning.py, scripts/tiebreak_sensitivity.py):
+ * bit 0: H prefers I over D on ties (default D over I); bit 1: a gap state tied between open and extend
+ * records "opened" (default: extend); bit 2: the end cell scans the last row before the last column
+ * (default: column first); bit 3: H prefers the gap states over the diagonal on ties.
+ * 0 = the documented choices above. Every variant is an optimal alignment: only co-optimal paths differ.
+ */
+static int g_tiebreak = 0;
+void oracle_sg_set_tiebreak(int v) { g_tiebreak = v; }
+int oracle_sg_get_tiebreak(void) { return g_tiebreak; }
+
 static inline int sub_score(char a, char b, int match, int mismatch)
 {
     int ok = (a == 'A' || a == 'C' || a == 'G' || a == 'T');
@@ -88,25 +99,42 @@ int oracle_sg_align(const char *s1, int n1, const char *s2, int n2,
             uint8_t t = 0;
             int i_open = up - open, i_ext = I[j] - ext;
             int vi;
-            if (i_open > i_ext) { vi = i_open; t |= T_I_OPEN; } else vi = i_ext;
+            const int open_on_tie = (g_tiebreak & 2) != 0;
+            if (i_open > i_ext || (open_on_tie && i_open == i_ext)) { vi = i_open; t |= T_I_OPEN; } else vi = i_ext;
             I[j] = vi;
             int d_open = left - open, d_ext = D - ext;
-            if (d_open > d_ext) { D = d_open; t |= T_D_OPEN; } else D = d_ext;
+            if (d_open > d_ext || (open_on_tie && d_open == d_ext)) { D = d_open; t |= T_D_OPEN; } else D = d_ext;
             int hd = diag + sub_score(s1[i - 1], s2[j - 1], match, mismatch);
             int h = hd;
             if (D > h) h = D;
             if (vi > h) h = vi;
-            if (h == hd) t |= T_DIAG; else if (h == D) t |= T_D; else t |= T_I;
+            if (g_tiebreak & 8) {
+                if ((g_tiebreak & 1) ? (h == vi) : (h == D)) t |= (g_tiebreak & 1) ? T_I : T_D;
+                else if ((g_tiebreak & 1) ? (h == D) : (h == vi)) t |= (g_tiebreak & 1) ? T_D : T_I;
+                else t |= T_DIAG;
+            } else if (h == hd) t |= T_DIAG;
+            else if (g_tiebreak & 1) { if (h == vi) t |= T_I; else t |= T_D; }
+            else { if (h == D) t |= T_D; else t |= T_I; }
             trow[j - 1] = t;
             diag = up;
             left = h;
             H[j] = h;
         }
         /* last column of this row */
-        if (H[n2] > best) { best = H[n2]; bi = i - 1; bj = n2 - 1; }
+        if (!(g_tiebreak & 4) && H[n2] > best) { best = H[n2]; bi = i - 1; bj = n2 - 1; }
+        if ((g_tiebreak & 4) && i < n1 && H[n2] > best) { best = H[n2]; bi = i - 1; bj = n2 - 1; }     /* provisional */
     }
-    for (int j = 1; j <= n2; ++j)
-        if (H[j] > best) { best = H[j]; bi = n1 - 1; bj = j - 1; }
+    if (g_tiebreak & 4) {
+        /* last row first (j ascending), then the last column (i ascending), strictly greater replaces */
+        int b2 = NEG_INF, i2 = -1, j2 = -1;
+        for (int j = 1; j <= n2; ++j)
+            if (H[j] > b2) { b2 = H[j]; i2 = n1 - 1; j2 = j - 1; }
+        if (best > b2) { /* a last-column cell of an earlier row is strictly better */ }
+        else { best = b2; bi = i2; bj = j2; }
+    } else {
+        for (int j = 1; j <= n2; ++j)
+            if (H[j] > best) { best = H[j]; bi = n1 - 1; bj = j - 1; }
+    }
 
     /* traceback, ops collected in reverse */
     char *rev = (char *)malloc((size_t)n1 + (size_t)n2 + 2);
