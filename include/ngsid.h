@@ -61,9 +61,12 @@ int ngsid_set_option(ngsid_ctx *ctx, int option, int value);
 
 /* ---- read upload ---------------------------------------------------------------------------
  * seq / qual: ASCII bases and PHRED+33 qualities of n_reads reads, concatenated; offsets has
- * n_reads+1 entries (offsets[0] == 0). Copies host->device, packs bases 2 bit/base on the device
+ * n_reads+1 entries (offsets[0] == 0). Copies host->device and packs bases 2 bit/base on the device
  * (A,C,G,T = 0..3; first base in the most significant bits of each 32-bit word; every read starts
- * on a word boundary) and rejects any other character with NGSID_EUNSUPPORTED.
+ * on a word boundary). Reads with any other character (N, IUPAC codes, lower case) are legal, as in
+ * the reference, which compares raw characters: their minimizers come from an exact exception path
+ * (see ngsid_kmer_string), alignments score such a base as a mismatch and the block statistic
+ * compares the raw characters.
  * Replaces nothing in the reference (its reads are Python str); it is the layout the kernels read.
  * A new upload discards all per-read results of the previous one.                              */
 int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint8_t *qual,
@@ -84,6 +87,11 @@ int ngsid_minimizers_timed(ngsid_ctx *ctx, int k, int w, int iters, float *avg_m
 int ngsid_get_minimizers(ngsid_ctx *ctx, int64_t begin, int64_t end, uint32_t *len_c,
                          uint32_t *counts, uint32_t *kmer, uint32_t *pos, int64_t cap,
                          int64_t *n_total);
+
+/* The string behind a minimizer code of the exception path: a k-mer with a base outside ACGT has the code
+ * 1 << 30 | index into a per-context dictionary (equal strings, equal codes; valid until the next
+ * upload). Returns the length, the string is NUL terminated.                                       */
+int ngsid_kmer_string(ngsid_ctx *ctx, uint32_t code, char *out, int cap);
 
 /* ---- K0: quality statistics ----------------------------------------------------------------
  * Replaces: modules/cluster.py:273-292 (per-run best quality, compressed error rate) and the
@@ -136,6 +144,15 @@ int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params, const int3
                   int64_t n_order, const int32_t *init_reps, int64_t n_init,
                   const uint32_t *acc_rank, int32_t *out_assign, uint8_t *out_via,
                   ngsid_cluster_stats *stats);
+
+/* ---- K2 alone: the hit table ------------------------------------------------------------------
+ * Replaces: cluster.get_all_hits (modules/cluster.py:43-62) for every (read, representative) pair: a
+ * table is built from the minimizers of `reps` (a k-mer once per representative, cluster.py:330-334),
+ * every minimizer of reads[i] is looked up (a read does not hit itself) and out_count[i * n_reps + r] /
+ * out_possum[i * n_reps + r] receive the number of hits and the sum of the hit positions -- the keys of
+ * the ranking at cluster.py:79. Inspection / test entry; ngsid_cluster does the same inside its pass. */
+int ngsid_hit_counts(ngsid_ctx *ctx, const int32_t *reps, int64_t n_reps, const int32_t *reads, int64_t n,
+                     uint32_t *out_count, uint32_t *out_possum);
 
 /* ---- K4 alone: semi-global block alignment statistic ----------------------------------------
  * Replaces: cluster.parasail_block_alignment (modules/cluster.py:130-169): parasail

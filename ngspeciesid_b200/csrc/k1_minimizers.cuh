@@ -12,7 +12,7 @@
 // (k1_stream_kernel compresses whole words).
 __global__ void k_pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off,
                               const int64_t *__restrict__ woff, uint32_t *__restrict__ packed,
-                              int64_t n_reads, int *__restrict__ bad_flag)
+                              int64_t n_reads, int *__restrict__ bad_flag, uint8_t *__restrict__ read_flag)
 {
     int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -30,7 +30,7 @@ __global__ void k_pack_kernel(const uint8_t *__restrict__ seq, const int64_t *__
                 int b = min(base + t, L - 1);
                 uint32_t c = s[b];
                 bool ok = (c == 'A') | (c == 'C') | (c == 'G') | (c == 'T');
-                if (!ok) *bad_flag = 1;
+                if (!ok) { *bad_flag = 1; read_flag[r] = 1; }
                 uint32_t code = ((c >> 1) & 3u) ^ ((c >> 2) & 1u);
                 word |= code << (30 - 2 * t);
             }

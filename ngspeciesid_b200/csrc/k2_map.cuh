@@ -479,3 +479,30 @@ __global__ void k2_iota_kernel(int32_t *list, int first, int n)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) list[i] = first + i;
 }
+
+// ---- stand-alone hit table: cluster.get_all_hits (modules/cluster.py:43-62) for (read, representative slot)
+// pairs: hit count and sum of hit positions, what the ranking of cluster.py:79 uses. One warp per read.
+__global__ void k2_hits_kernel(MapTable t, const int32_t *__restrict__ reads, int n_reads, int n_slots,
+                               const Minimizer *__restrict__ mins, const int64_t *__restrict__ moff,
+                               const uint32_t *__restrict__ nmin, const int32_t *__restrict__ slot_read,
+                               uint32_t *__restrict__ out_cnt, uint32_t *__restrict__ out_possum)
+{
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= n_reads) return;
+    const uint32_t lane = lane_id();
+    const int read = reads[warp];
+    const Minimizer *m = mins + moff[read];
+    const int nm = (int)nmin[read];
+    for (int j = lane; j < nm; j += 32) {
+        const Minimizer mj = m[j];
+        int32_t node = table_lookup(t, mj.x);
+        while (node >= 0) {
+            const PostingNode pn = t.nodes[node];
+            if (slot_read[pn.slot] != read) {                    // a read does not hit itself (cluster.py:52)
+                atomicAdd(&out_cnt[(size_t)warp * n_slots + pn.slot], 1u);
+                atomicAdd(&out_possum[(size_t)warp * n_slots + pn.slot], mj.y);
+            }
+            node = pn.next;
+        }
+    }
+}

@@ -123,7 +123,7 @@ k4_align_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off
         const uint8_t *s2 = seq + off[rb];
         const int n1 = (int)(off[ra + 1] - off[ra]);
         const int n2 = (int)(off[rb + 1] - off[rb]);
-        for (int j = lane; j < n2; j += 32) s2s[j] = s2[j];
+        for (int j = lane; j < n2; j += 32) s2s[j] = k4_col_base(s2[j]);
         __syncwarp();
 
         // best cell of the last column (rows ascending, strictly greater replaces)
@@ -139,7 +139,7 @@ k4_align_kernel(const uint8_t *__restrict__ seq, const int64_t *__restrict__ off
 #pragma unroll
             for (int r = 0; r < K4_RPL; ++r) {
                 int i = row0 + r;
-                R.c1[r] = (i < n1) ? (uint32_t)s1[i] : 0xffu;
+                R.c1[r] = (i < n1) ? k4_row_base(s1[i]) : 0xffu;
                 R.H[r] = 0;
                 R.D[r] = NGSID_NEG_INF;
                 R.PH[r] = k4_lead(i + 1, kc);

@@ -100,11 +100,11 @@ k4t_dp_kernel(K4TSeqs Q,
         const int n2 = Q.len(rb);
         uint32_t *tr = trace + (size_t)sl * slot_words;
         if (MULTI) {
-            for (int j = threadIdx.x; j < n2; j += blockDim.x) s2s[j] = s2[j];
+            for (int j = threadIdx.x; j < n2; j += blockDim.x) s2s[j] = k4_col_base(s2[j]);
             if (threadIdx.x < K4T_MAXW) prog[threadIdx.x] = 0;
             __syncthreads();
         } else {
-            for (int j = lane; j < n2; j += 32) s2s[j] = s2[j];
+            for (int j = lane; j < n2; j += 32) s2s[j] = k4_col_base(s2[j]);
             __syncwarp();
         }
 
@@ -125,7 +125,7 @@ k4t_dp_kernel(K4TSeqs Q,
 #pragma unroll
             for (int r = 0; r < K4T_RPL; ++r) {
                 int i = row0 + r;
-                c1[r] = (i < n1) ? (uint32_t)s1[i] : 0xffu;
+                c1[r] = (i < n1) ? k4_row_base(s1[i]) : 0xffu;
                 H[r] = 0;
                 D[r] = NGSID_NEG_INF;
             }

@@ -90,7 +90,7 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     ngsid_nccl_finalize(ctx);
-    DevBuf *bufs[] = {&ctx->d_seq, &ctx->d_qual, &ctx->d_off, &ctx->d_packed, &ctx->d_woff, &ctx->d_flag,
+    DevBuf *bufs[] = {&ctx->d_seq, &ctx->d_qual, &ctx->d_off, &ctx->d_packed, &ctx->d_woff, &ctx->d_flag, &ctx->d_rflag,
                       &ctx->d_moff, &ctx->d_mins, &ctx->d_nmin, &ctx->d_lenc, &ctx->d_errc, &ctx->d_erru,
                       &ctx->d_bucket, &ctx->d_phred, &ctx->d_thr, &ctx->d_keys, &ctx->d_heads, &ctx->d_nodes,
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
@@ -155,27 +155,36 @@ static int reads_layout(ngsid_ctx *ctx, const int64_t *offsets, int64_t n_reads)
     return NGSID_OK;
 }
 
-// 2-bit packing of the bases now in d_seq; rejects the read set when a base is outside ACGT.
+// 2-bit packing of the bases now in d_seq. Reads with a base outside ACGT are remembered: their
+// minimizers come from the exception path (k1_exceptions.cuh), everything else treats their bases as
+// the raw characters the reference compares.
 static int reads_finish(ngsid_ctx *ctx)
 {
     const int64_t n_reads = ctx->n_reads;
     if (n_reads == 0) return NGSID_OK;
+    CUDA_TRY(ctx, ctx->d_rflag.ensure((size_t)n_reads + 64));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_flag.p, 0, 64, ctx->stream));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_rflag.p, 0, (size_t)n_reads, ctx->stream));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_packed.p, 0, (size_t)ctx->total_words * 4 + 64, ctx->stream));
     int blocks = (int)std::min<int64_t>((n_reads + 7) / 8, (int64_t)ctx->sm_count * 16);
     cudaEventRecord(ctx->pev[0][0], ctx->stream);
     k_pack_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_seq.as<uint8_t>(), ctx->d_off.as<int64_t>(),
                                                    ctx->d_woff.as<int64_t>(), ctx->d_packed.as<uint32_t>(),
-                                                   n_reads, ctx->d_flag.as<int>());
+                                                   n_reads, ctx->d_flag.as<int>(), ctx->d_rflag.as<uint8_t>());
     cudaEventRecord(ctx->pev[0][1], ctx->stream);
     ctx->pev_valid[0] = true;
     KERNEL_CHECK(ctx);
     int flag = 0;
     CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->x_reads.clear();
+    ctx->xkmers.clear();
+    ctx->xkmer_id.clear();
     if (flag) {
-        ctx->n_reads = 0;
-        return fail(ctx, NGSID_EUNSUPPORTED, "a read contains a base outside ACGT (unsupported in this build)");
+        std::vector<uint8_t> rf((size_t)n_reads);
+        CUDA_TRY(ctx, cudaMemcpyAsync(rf.data(), ctx->d_rflag.p, (size_t)n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int64_t r = 0; r < n_reads; ++r) if (rf[r]) ctx->x_reads.push_back((int32_t)r);
     }
     return NGSID_OK;
 }
@@ -284,6 +293,8 @@ static int k1_launch(ngsid_ctx *ctx)
     return k1_launch_generic(ctx, slow_list, slow_n, std::min<int64_t>(ctx->n_reads, 4096));
 }
 
+#include "k1_exceptions.cuh"
+
 extern "C" int ngsid_minimizers(ngsid_ctx *ctx, int k, int w)
 {
     if (!ctx) return NGSID_EINVAL;
@@ -295,6 +306,8 @@ extern "C" int ngsid_minimizers(ngsid_ctx *ctx, int k, int w)
     rc = k1_launch(ctx);
     cudaEventRecord(ctx->pev[1][1], ctx->stream);
     ctx->pev_valid[1] = true;
+    if (rc) return rc;
+    rc = k1_exceptions(ctx);
     if (rc) return rc;
     ctx->have_min = true;
     ctx->h_nmin_valid = false;
@@ -315,6 +328,8 @@ extern "C" int ngsid_minimizers_timed(ngsid_ctx *ctx, int k, int w, int iters, f
     }
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev1));
+    rc = k1_exceptions(ctx);
+    if (rc) return rc;
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     *avg_ms = ms / iters;
@@ -557,7 +572,7 @@ static int k4t_run(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const i
 static int k4_dispatch(ngsid_ctx *ctx, const int32_t *pa, const int32_t *pb, const int32_t *po, const int32_t *pm,
                        int stride, int64_t n_pairs, int k, int32_t *out_count, int32_t *out_score)
 {
-    if (ctx->use_payload_k4) return k4_launch(ctx, pa, pb, po, pm, stride, n_pairs, k, out_count, out_score);
+    if (ctx->use_payload_k4 && ctx->x_reads.empty()) return k4_launch(ctx, pa, pb, po, pm, stride, n_pairs, k, out_count, out_score);
     return k4t_run(ctx, pa, pb, po, pm, stride, n_pairs, k, ctx->max_len, ctx->max_len, false,
                    out_count, out_score, nullptr, nullptr, nullptr, 500);
 }
@@ -1184,6 +1199,47 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     }
     if (stats) *stats = R.st;
     return cleanup(NGSID_OK);
+}
+
+// ---- stand-alone hit table (test / inspection entry): see include/ngsid.h
+extern "C" int ngsid_hit_counts(ngsid_ctx *ctx, const int32_t *reps, int64_t n_reps, const int32_t *reads, int64_t n,
+                                uint32_t *out_count, uint32_t *out_possum)
+{
+    if (!ctx || n_reps < 0 || n < 0 || (n_reps > 0 && !reps) || (n > 0 && (!reads || !out_count || !out_possum))) return NGSID_EINVAL;
+    if (!ctx->have_min) return fail(ctx, NGSID_ESTATE, "ngsid_minimizers has not run");
+    for (int64_t i = 0; i < n_reps; ++i) if (reps[i] < 0 || reps[i] >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "representative out of range");
+    for (int64_t i = 0; i < n; ++i) if (reads[i] < 0 || reads[i] >= ctx->n_reads) return fail(ctx, NGSID_EINVAL, "read out of range");
+    if (n == 0 || n_reps == 0) return NGSID_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = fetch_nmin(ctx);
+    if (rc) return rc;
+    int64_t pairs = 0;
+    for (int64_t i = 0; i < n_reps; ++i) pairs += ctx->h_nmin[reps[i]];
+    uint32_t cap = 1u << 12;
+    while ((int64_t)cap < pairs * 4) cap <<= 1;
+    DevBuf keys, heads, nodes, cursor, err, d_reps, d_reads, d_cnt, d_sum;
+    auto done = [&](int code) { DevBuf *b[] = {&keys, &heads, &nodes, &cursor, &err, &d_reps, &d_reads, &d_cnt, &d_sum}; for (DevBuf *x : b) x->release(); return code; };
+#define HC_TRY(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { ctx->err = cudaGetErrorString(_e); return done(NGSID_ECUDA); } } while (0)
+    HC_TRY(keys.ensure((size_t)cap * 4)); HC_TRY(heads.ensure((size_t)cap * 4)); HC_TRY(nodes.ensure((size_t)(pairs + 1) * sizeof(PostingNode)));
+    HC_TRY(cursor.ensure(64)); HC_TRY(err.ensure(64)); HC_TRY(d_reps.ensure((size_t)n_reps * 4)); HC_TRY(d_reads.ensure((size_t)n * 4));
+    HC_TRY(d_cnt.ensure((size_t)n * n_reps * 4)); HC_TRY(d_sum.ensure((size_t)n * n_reps * 4));
+    HC_TRY(cudaMemsetAsync(keys.p, 0xff, (size_t)cap * 4, ctx->stream)); HC_TRY(cudaMemsetAsync(heads.p, 0xff, (size_t)cap * 4, ctx->stream));
+    HC_TRY(cudaMemsetAsync(cursor.p, 0, 64, ctx->stream)); HC_TRY(cudaMemsetAsync(err.p, 0, 64, ctx->stream));
+    HC_TRY(cudaMemsetAsync(d_cnt.p, 0, (size_t)n * n_reps * 4, ctx->stream)); HC_TRY(cudaMemsetAsync(d_sum.p, 0, (size_t)n * n_reps * 4, ctx->stream));
+    HC_TRY(cudaMemcpyAsync(d_reps.p, reps, (size_t)n_reps * 4, cudaMemcpyHostToDevice, ctx->stream));
+    HC_TRY(cudaMemcpyAsync(d_reads.p, reads, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MapTable t = {keys.as<uint32_t>(), heads.as<int32_t>(), nodes.as<PostingNode>(), cap - 1};
+    k2_insert_kernel<<<(unsigned)((n_reps + 7) / 8), 256, 0, ctx->stream>>>(t, cursor.as<int32_t>(), (int32_t)(pairs + 1), err.as<int32_t>(), d_reps.as<int32_t>(),
+                                                                        0, (int)n_reps, ctx->d_mins.as<Minimizer>(), ctx->d_moff.as<int64_t>(), ctx->d_nmin.as<uint32_t>());
+    k2_hits_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(t, d_reads.as<int32_t>(), (int)n, (int)n_reps, ctx->d_mins.as<Minimizer>(), ctx->d_moff.as<int64_t>(),
+                                                                     ctx->d_nmin.as<uint32_t>(), d_reps.as<int32_t>(), d_cnt.as<uint32_t>(), d_sum.as<uint32_t>());
+    ctx->launches += 2;
+    HC_TRY(cudaGetLastError());
+    HC_TRY(cudaMemcpyAsync(out_count, d_cnt.p, (size_t)n * n_reps * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HC_TRY(cudaMemcpyAsync(out_possum, d_sum.p, (size_t)n * n_reps * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HC_TRY(cudaStreamSynchronize(ctx->stream));
+#undef HC_TRY
+    return done(NGSID_OK);
 }
 
 #include "nccl_plane.cuh"

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "../../include/ngsid.h"
 
@@ -71,7 +72,12 @@ struct ngsid_ctx {
     int max_len = 0;
     std::vector<int64_t> h_off;       // n+1 byte offsets
     std::vector<int64_t> h_woff;      // n+1 word offsets of the packed reads
-    DevBuf d_seq, d_qual, d_off, d_packed, d_woff, d_flag;
+    DevBuf d_seq, d_qual, d_off, d_packed, d_woff, d_flag, d_rflag;
+    // reads with a base outside ACGT (exception path of K1, csrc/k1_exceptions.cuh) and the k-mers with such
+    // a base that became minimizers: code = 1 << 30 | index into xkmers
+    std::vector<int32_t> x_reads;
+    std::vector<std::string> xkmers;
+    std::unordered_map<std::string, uint32_t> xkmer_id;
 
     // ---- K1 results
     int k = 0, w = 0;
@@ -130,3 +136,11 @@ static inline int fail(ngsid_ctx *ctx, int code, const std::string &msg) {
 }
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+// Alignment scoring of bases outside ACGT: the reference scores with parasail.matrix_create("ACGT", 2, -2)
+// (modules/cluster.py:131), where such a base is a mismatch against everything, itself included. Rows and
+// columns map them to two different sentinels, so the DP's equality test never fires for them. (The block
+// statistic compares the raw characters, modules/cluster.py:147, so the traceback reads the raw bases.)
+__device__ __forceinline__ bool k4_is_acgt(uint32_t c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+__device__ __forceinline__ uint32_t k4_row_base(uint32_t c) { return k4_is_acgt(c) ? c : 0xfeu; }
+__device__ __forceinline__ uint8_t k4_col_base(uint32_t c) { return (uint8_t)(k4_is_acgt(c) ? c : 0xfdu); }

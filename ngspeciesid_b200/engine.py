@@ -195,6 +195,14 @@ class Engine(object):
                                            ctypes.byref(st)))
         return assign, via, st.as_dict()
 
+    def hit_counts(self, reps, reads):
+        """get_all_hits for every (read, representative) pair -> (counts, position sums), shape (len(reads), len(reps))."""
+        reps, reads = as_array(reps, np.int32), as_array(reads, np.int32)
+        cnt = np.zeros((len(reads), len(reps)), dtype=np.uint32)
+        psum = np.zeros((len(reads), len(reps)), dtype=np.uint32)
+        self._check(self.lib.ngsid_hit_counts(self.h, ptr(reps), len(reps), ptr(reads), len(reads), ptr(cnt), ptr(psum)))
+        return cnt, psum
+
     # ---- K4 alone
     def sg_block_align(self, read_a, read_b, open_pen, match_id, k, want_score=False):
         a, b = as_array(read_a, np.int32), as_array(read_b, np.int32)
@@ -332,6 +340,18 @@ class Engine(object):
 
     def set_option(self, option, value):
         self._check(self.lib.ngsid_set_option(self.h, option, value))
+
+    def kmer_string(self, code, k):
+        """The k-mer string behind a minimizer code, including codes of the exception path (k-mers with a
+        base outside ACGT: 1 << 30 | dictionary index)."""
+        code = int(code)
+        if code & (1 << 30) and not code & (1 << 31):
+            buf = ctypes.create_string_buffer(256)
+            n = self.lib.ngsid_kmer_string(self.h, code, buf, 256)
+            if n < 0:
+                self._check(n)
+            return buf.value.decode("ascii")
+        return decode_kmer(code, k)
 
     def poa_cells(self):
         """DP cells (graph rows x layer bases, summed) of the last poa_consensus call."""

@@ -18,9 +18,9 @@ def _hpol(seq):
 
 def get_kmer_minimizers(seq, k_size, w_size):
     """Reference: modules/cluster.py:16-39. `seq` is the (already homopolymer-compressed) string;
-    returns [(kmer, position)]. The kernel compresses its input itself, which is the identity on
-    a compressed string; inputs that still contain homopolymers are handled by doubling... no:
-    they are rejected, because the reference would treat them differently."""
+    returns [(kmer, position)]. The kernel compresses its input itself, which is the identity on a
+    compressed string; a string that still contains homopolymers is rejected, because the reference
+    would not compress it."""
     if _hpol(seq) != seq:
         raise ValueError("get_kmer_minimizers expects a homopolymer-compressed sequence "
                          "(the reference only ever passes seq_hpol_comp, modules/cluster.py:269)")
@@ -28,7 +28,7 @@ def get_kmer_minimizers(seq, k_size, w_size):
     eng.upload_records([(seq, "I" * len(seq))])
     eng.minimizers(k_size, w_size)
     _lc, _cnt, kmer, pos = eng.get_minimizers(0, 1)
-    return [(_engine.decode_kmer(c, k_size), int(p)) for c, p in zip(kmer, pos)]
+    return [(eng.kmer_string(c, k_size), int(p)) for c, p in zip(kmer, pos)]
 
 
 def p_shared_minimizer_empirical(error_rate_read, error_rate_center, p_emp_probs):
@@ -115,7 +115,7 @@ def reads_to_clusters(clusters, representatives, sorted_reads, p_emp_probs, mini
                 representatives[rid] = (rid, new_batch_index, acc, seq, qual, score, float(err_c[0]), _hpol(seq))
             _lc, _cnt, kmer, _pos = eng.get_minimizers(li, li + 1)
             for c in kmer:
-                m = _engine.decode_kmer(c, k)
+                m = eng.kmer_string(c, k)
                 s = minimizer_database.get(m)
                 if s is None:
                     minimizer_database[m] = s = set()

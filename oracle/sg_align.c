@@ -149,9 +149,9 @@ int oracle_sg_align(const char *s1, int n1, const char *s2, int n2,
         uint8_t t = trace[(size_t)i * (size_t)n2 + (size_t)j];
         if (where == T_DIAG) {
             if (t & T_DIAG) {
-                char a = s1[i], b = s2[j];
-                int ok = (a == 'A' || a == 'C' || a == 'G' || a == 'T');
-                rev[c++] = (ok && a == b) ? '=' : 'X';
+                /* '=' by character equality (what the reference's statistic compares, modules/cluster.py:147);
+                   the SCORE of a base outside ACGT is a mismatch even against itself (sub_score) */
+                rev[c++] = (s1[i] == s2[j]) ? '=' : 'X';
                 --i; --j;
             } else if (t & T_D) where = T_D;
             else where = T_I;

@@ -159,11 +159,66 @@ def test_error_codes(eng, p_table):
     with pytest.raises(NgsidError) as ei:
         eng.sg_block_align([0], [5], [3], [5], 13)
     assert ei.value.code == -1
-    with pytest.raises(NgsidError):
-        eng.upload_records([("ACGTRYACGT", "5555555555")])
+    eng.upload_records([("ACGTRYACGT", "5555555555")])              # bases outside ACGT are legal input (exception path)
     # the context is still usable after every error
     eng.upload_records([(s, "5" * 200), (s, "5" * 200)])
     eng.minimizers(13, 20)
     eng.quality_stats()
     a, _v, _st = eng.cluster(13, 20, mg, np.arange(2), E.accession_ranks(["a", "b"]))
     assert list(a) == [-1, 0]
+
+
+def test_reads_with_bases_outside_acgt(eng, p_table):
+    """the reference compares raw characters (modules/cluster.py:19-37, 265), so N, IUPAC
+    codes and lower-case bases are legal: they order by character code in the minimizers, are table keys
+    like any k-mer, never match in the alignment score (parasail's ACGT matrix) but do count as equal
+    columns in the block statistic. Minimizers, alignment statistic and cluster assignments = oracle."""
+    from ngspeciesid_b200 import engine as E
+    from ngspeciesid_b200.synth import simulate_reads
+    rng = np.random.default_rng(123)
+    recs = list(simulate_reads(300, n_species=3, len_lo=350, len_hi=420, seed=9).records())
+    mutated = []
+    for n, (acc, s, q) in enumerate(recs):
+        s = list(s)
+        if n % 3 == 0:                                  # a third of the reads carry a few such bases
+            for _ in range(int(rng.integers(1, 6))):
+                p = int(rng.integers(0, len(s)))
+                s[p] = "NNNRYacgtn"[int(rng.integers(10))]
+        if n % 50 == 0:                                 # and a run of N (compresses to one N)
+            p = int(rng.integers(20, len(s) - 20))
+            s[p:p + 6] = list("NNNNNN")
+        mutated.append((acc, "".join(s), q))
+    ra = oc.read_array_from_sorted(oc.sort_stage(mutated, 13))
+    eng.upload_records([(r[3], r[4]) for r in ra])
+    eng.minimizers(13, 20)
+    eng.quality_stats()
+    len_c, counts, kmer, pos = eng.get_minimizers()
+    o = 0
+    n_special = 0
+    for i, r in enumerate(ra):
+        seqc, _ = oc.hpol_compress(r[3])
+        exp = oc.minimizers(seqc, 13, 20)
+        got = [(eng.kmer_string(kmer[o + j], 13), int(pos[o + j])) for j in range(counts[i])]
+        assert len_c[i] == len(seqc) and got == exp, i
+        n_special += sum(1 for km, _p in exp if set(km) - set("ACGT"))
+        o += counts[i]
+    assert n_special > 20
+    # alignment statistic on pairs that contain such bases on both sides
+    a = [i for i in range(len(ra)) if set(ra[i][3]) - set("ACGT")][:40]
+    b = a[1:] + a[:1]
+    cnt, score = eng.sg_block_align(a, b, [3] * len(a), [9] * len(a), 13, want_score=True)
+    for x, y, c, sc in zip(a, b, cnt, score):
+        ops, esc = co_align(ra[x][3], ra[y][3], 3)
+        assert sc == esc and c == oc._lib().oracle_block_count(ops.encode(), len(ops), 13, 9)
+    # the whole pass
+    p_emp = oc.load_p_emp(p_table, 13, 20)
+    stats = oc.Stats()
+    oc.single_clustering(ra, p_emp, oc.default_args(), stats)
+    exp = [w for _r, w, _h in stats.trace]
+    assign, _via, _st = eng.cluster(13, 20, E.max_gap_table(p_emp, 0.1), np.arange(len(ra)), E.accession_ranks([r[2] for r in ra]))
+    assert list(assign) == exp
+
+
+def co_align(s1, s2, open_pen):
+    from oracle import consensus_oracle as co
+    return co.align_ops(s1, s2, open_pen)

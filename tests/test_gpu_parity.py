@@ -617,3 +617,32 @@ def test_slot_and_node_pools_grow(eng, p_table, seed, monkeypatch):
     recs = _mixed_reads(600, seed)
     st, _ = _cluster_vs_oracle(eng, p_table, recs, tile=32)
     assert st["n_new_reps"] > 60
+
+
+def test_hit_table_matches_get_all_hits(eng):
+    """Stand-alone test of the hit table: per (read, representative) the number of read
+    minimizers whose k-mer the representative holds and the sum of their positions, against a direct
+    restatement of cluster.get_all_hits (modules/cluster.py:43-62) on the oracle's minimizers."""
+    recs = scenario_reads("supp1k")[:400]
+    eng.upload_records([(s, q) for _a, s, q in recs])
+    eng.minimizers(13, 20)
+    mins = []
+    for _a, s, _q in recs:
+        seqc, _ = oc.hpol_compress(s)
+        mins.append(oc.minimizers(seqc, 13, 20) if len(seqc) >= 13 else [])
+    reps = list(range(0, 400, 9))
+    reads = list(range(400))
+    cnt, psum = eng.hit_counts(reps, reads)
+    db = {}
+    for r in reps:
+        for km, _p in mins[r]:
+            db.setdefault(km, set()).add(r)
+    col = {r: c for c, r in enumerate(reps)}
+    exp_c = np.zeros_like(cnt); exp_s = np.zeros_like(psum)
+    for i in reads:
+        for km, p in mins[i]:
+            for r in db.get(km, ()):
+                if r != i:
+                    exp_c[i, col[r]] += 1; exp_s[i, col[r]] += p
+    assert (cnt == exp_c).all() and (psum == exp_s).all()
+    assert exp_c.max() > 50 and (exp_c > 0).sum() > 2000
