@@ -89,10 +89,14 @@ def test_k1_minimizers_edge_cases(eng):
     _check_minimizers(eng, seqs, 5, 9)
 
 
-def test_k1_rejects_non_acgt(eng):
-    from ngspeciesid_b200._lib import NgsidError
-    with pytest.raises(NgsidError):
-        eng.upload_records([("ACGTNACGT", "555555555")])
+def test_k1_accepts_non_acgt(eng):
+    """Bases outside ACGT go through the exception path (tests/test_gpu_edge_cases.py has the full check)."""
+    s = "ACGTNACGTTGCANNACGATCGATCGGCTAGCTAGCTAGGATCGATCGTAGCTAGCTAGCTAGCTAGGGCTA"
+    eng.upload_records([(s, "5" * len(s))])
+    eng.minimizers(13, 20)
+    len_c, counts, kmer, pos = eng.get_minimizers()
+    seqc, _ = oc.hpol_compress(s)
+    assert [(eng.kmer_string(c, 13), int(p)) for c, p in zip(kmer, pos)] == oc.minimizers(seqc, 13, 20)
 
 
 @pytest.mark.parametrize("tag", ["h1", "supp1k", "synth2k"])
