@@ -50,9 +50,10 @@ __device__ __forceinline__ uint32_t k1s_min(uint32_t a, uint32_t b) { return min
 #endif
 
 #define K1S_THREADS 128
-#define K1S_GROUP 8                 // reads per extraction group in phase C
-#define K1S_WARP_EXTRA (4 * (K1S_GROUP + 2) + 8 * K1S_GROUP)   // per warp: read starts + output bases
+#define K1S_GROUP 4                 // reads per extraction group in phase C
+#define K1S_WARP_EXTRA 32           // per warp: read starts of a group (K1S_GROUP + 1 words), 16-byte multiple
 #define K1S_SLOTS 9                 // straight-line extraction slots per bitmap word
+#define K1S_IPL 3                   // bitmap words per lane and extraction pass
 #define K1S_SMEM_LIMIT (160 * 1024)  // above this the read set goes to the ring / generic kernels
 
 #ifdef K1S_HOST
@@ -86,7 +87,7 @@ uint32_t k1s_lut_entry(uint32_t idx)
 struct K1SGeom {
     int n_it_max;      // steps of 32 k-mers the longest possible read needs
     int sw, bw, rs;    // stream words, bitmap words, region stride
-    int scap;          // staged positions per extraction group (u16 each); overflow -> generic kernel
+    int scap;          // staged records per extraction group (8 bytes each, even); overflow -> generic kernel
 };
 static inline K1SGeom k1s_geometry(int max_len, int k)
 {
@@ -100,15 +101,18 @@ static inline K1SGeom k1s_geometry(int max_len, int k)
     g.bw = g.n_it_max + 2;
     g.rs = g.sw + g.bw;
     if ((g.rs & 1) == 0) g.rs++;
-    // expected density is ~0.22 minimizers per k-mer; 0.3 leaves headroom, overflow is handled
-    g.scap = (K1S_GROUP * g.n_it_max * 32 / 4 + 63) / 64 * 64;     // 0.25 per k-mer slot of the region
-    if (g.scap < 256) g.scap = 256;
+    // records of a group are staged in shared memory before they leave as one bulk store per read.
+    // Expected density is ~0.22 minimizers per k-mer of the ACTUAL read (regions are sized for the longest
+    // read at 85 % compression); 0.195 per k-mer slot of the region keeps four blocks per SM at 800 bases
+    // and leaves ~3 sigma of headroom; a group that does not fit goes to the generic kernel.
+    g.scap = ((K1S_GROUP * g.n_it_max * 32 * 39 / 200) / 2) * 2;
+    if (g.scap < 128) g.scap = 128;
     return g;
 }
 static inline size_t k1s_smem_bytes(const K1SGeom &g)
 {
     // table | regions | per warp: staging + read starts
-    return 1024 * 4 + (size_t)K1S_THREADS * g.rs * 4 + (size_t)(K1S_THREADS / 32) * ((size_t)g.scap * 2 + K1S_WARP_EXTRA);
+    return 1024 * 4 + ((size_t)K1S_THREADS * g.rs * 4 + 15) / 16 * 16 + (size_t)(K1S_THREADS / 32) * ((size_t)g.scap * 8 + K1S_WARP_EXTRA);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -380,104 +384,138 @@ k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict_
     }
     __syncwarp();
 
-    // ---- phase C: bitmaps -> ordered positions -> records, K1S_GROUP reads at a time.
-    // One warp instruction here serves 32 records of ONE read (phases A and B serve 32 reads), so
-    // this part is written against the instruction count: 32-bit shared addresses, one staged u16
-    // per record at a compile-time offset from the lane's first slot, no per-record bounds checks.
+    // ---- phase C: bitmaps -> records, K1S_GROUP reads at a time.
+    // One warp instruction here serves 32 bitmap words of a few reads (phases A and B serve 32 reads), so this
+    // part is written against the instruction count. A lane takes K1S_IPL consecutive bitmap words, a warp scan
+    // of their popcounts gives every word the index of its first record, and the lane writes its records
+    // (k-mer code re-read from the compressed stream, position) straight into the group's staging area in
+    // shared memory, read after read (each read starts on a 16-byte boundary). The staged records of a read
+    // then leave as ONE bulk copy shared -> global issued by the read's own lane (cp.async.bulk, the TMA
+    // engine does the coalescing); the wait for the engine's reads of the staging area sits behind the next
+    // group's popcount scan.
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(k1s_smem);
     const uint32_t rsb = (uint32_t)rs * 4u;
     const uint32_t s_wreg = s_base + 4096u + (uint32_t)(wid * 32) * rsb;          // this warp's 32 regions
-    const uint32_t s_stage = s_base + 4096u + (uint32_t)K1S_THREADS * rsb + (uint32_t)wid * (2u * (uint32_t)scap + K1S_WARP_EXTRA);
-    const uint32_t s_rstart = s_stage + 2u * (uint32_t)scap;
-    const uint32_t s_tbl = s_rstart + 4u * (K1S_GROUP + 2);                          // 8-byte aligned
+    const uint32_t s_stage = s_base + 4096u + (((uint32_t)K1S_THREADS * rsb + 15u) & ~15u) + (uint32_t)wid * (8u * (uint32_t)scap + K1S_WARP_EXTRA);
+    const uint32_t s_rstart = s_stage + 8u * (uint32_t)scap;
     const uint32_t bm_off = (uint32_t)sw * 4u;
     const int kshift = 32 - 2 * k;
-    // extraction: two consecutive bitmap words per lane and pass (two independent extraction
-    // chains per lane, one scan per 64 words)
-    const int dq = 64 / n_it, dc = 64 % n_it;
-    const int q0 = (2 * lane) / n_it, c0 = (2 * lane) % n_it;
     const int total_items = K1S_GROUP * n_it;
+    const int q_l = (K1S_IPL * lane) / n_it, c_l = (K1S_IPL * lane) % n_it;        // first item of this lane in a pass
+    const int dq = (32 * K1S_IPL) / n_it, dc = (32 * K1S_IPL) % n_it;              // advance per pass
     uint32_t my_n = 0;
     bool my_slow = have && !ok;
+    bool pending = false;                                                          // bulk copies of the previous group in flight
     for (int g0 = 0; g0 < 32; g0 += K1S_GROUP) {
         if (!__any_sync(NGSID_FULL_MASK, have && lane >= g0)) break;
-        int qa = q0, ca = c0;
+        // ---- pass 1: popcounts -> index of every word's first record, read starts
+        uint32_t mw[3][K1S_IPL], ow[3][K1S_IPL];                                   // up to 3 passes of 96 words (n_it <= 72)
+        int qw[3][K1S_IPL], cw[3][K1S_IPL];
         uint32_t run = 0;
-        for (int f0 = 0; f0 < total_items; f0 += 64) {
-            const int fa = f0 + 2 * lane;
-            const bool va = fa < total_items, vb = fa + 1 < total_items;
-            int qb = qa, cb = ca + 1;
-            if (cb >= n_it) { cb = 0; ++qb; }
-            uint32_t ma = 0, mb = 0;
-            if (va) ma = k1s_lds32(s_wreg + (uint32_t)(g0 + qa) * rsb + bm_off + 4u * (uint32_t)ca);
-            if (vb) mb = k1s_lds32(s_wreg + (uint32_t)(g0 + qb) * rsb + bm_off + 4u * (uint32_t)cb);
-            const uint32_t na = (uint32_t)__popc(ma), n = na + (uint32_t)__popc(mb);
+        int qa = q_l, ca = c_l;
+        int np_ = 0;
+        for (int f0 = 0; f0 < total_items && np_ < 3; f0 += 32 * K1S_IPL, ++np_) {
+            int q = qa, c = ca;
+            uint32_t n = 0;
+#pragma unroll
+            for (int t = 0; t < K1S_IPL; ++t) {
+                const bool v = f0 + K1S_IPL * lane + t < total_items;
+                mw[np_][t] = v ? k1s_lds32(s_wreg + (uint32_t)(g0 + q) * rsb + bm_off + 4u * (uint32_t)c) : 0u;
+                qw[np_][t] = q; cw[np_][t] = v ? c : -1;
+                n += (uint32_t)__popc(mw[np_][t]);
+                if (++c >= n_it) { c = 0; ++q; }
+            }
             uint32_t incl = n;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t v = __shfl_up_sync(NGSID_FULL_MASK, incl, d);
                 if (lane >= d) incl += v;
             }
-            const uint32_t oa = run + incl - n, ob = oa + na;
-            if (va && ca == 0) k1s_sts32(s_rstart + 4u * (uint32_t)qa, oa);
-            if (vb && cb == 0) k1s_sts32(s_rstart + 4u * (uint32_t)qb, ob);
-            run += __shfl_sync(NGSID_FULL_MASK, incl, 31);
-            if (oa + n > (uint32_t)scap) { ma = 0; mb = 0; }   // group overflow: its reads go to the slow list
-            uint32_t sa = s_stage + 2u * oa, sb = s_stage + 2u * ob;
-            const uint32_t pa = ((uint32_t)qa << 13) | ((uint32_t)ca << 5);   // read-in-group | position
-            const uint32_t pb = ((uint32_t)qb << 13) | ((uint32_t)cb << 5);
+            uint32_t o = run + incl - n;
 #pragma unroll
-            for (int s = 0; s < K1S_SLOTS; ++s) {
-                const uint32_t xa = k1s_clz(ma), xb = k1s_clz(mb);
-                if (ma != 0u) k1s_sts16(sa + 2u * s, pa + xa);
-                if (mb != 0u) k1s_sts16(sb + 2u * s, pb + xb);
-                ma &= k1s_fsr(0x7fffffffu, 0u, xa);         // clears bit 31 - x (the bits above it are 0)
-                mb &= k1s_fsr(0x7fffffffu, 0u, xb);
+            for (int t = 0; t < K1S_IPL; ++t) {
+                ow[np_][t] = o;
+                if (cw[np_][t] == 0) k1s_sts32(s_rstart + 4u * (uint32_t)qw[np_][t], o);
+                o += (uint32_t)__popc(mw[np_][t]);
             }
-            sa += 2u * K1S_SLOTS; sb += 2u * K1S_SLOTS;
-            while (__any_sync(NGSID_FULL_MASK, (ma | mb) != 0u)) {
-                const uint32_t xa = k1s_clz(ma), xb = k1s_clz(mb);
-                if (ma != 0u) { k1s_sts16(sa, pa + xa); sa += 2u; }
-                if (mb != 0u) { k1s_sts16(sb, pb + xb); sb += 2u; }
-                ma &= k1s_fsr(0x7fffffffu, 0u, xa);
-                mb &= k1s_fsr(0x7fffffffu, 0u, xb);
-            }
+            run += __shfl_sync(NGSID_FULL_MASK, incl, 31);
             ca += dc; qa += dq;
             if (ca >= n_it) { ca -= n_it; ++qa; }
         }
         if (lane == 0) k1s_sts32(s_rstart + 4u * K1S_GROUP, run);
         __syncwarp();
-        const bool overflow = run > (uint32_t)scap;
+        // per read of the group: first record (flat) and padding so that every read starts on 16 bytes
+        uint32_t rs_[K1S_GROUP + 1], pad_[K1S_GROUP];
+#pragma unroll
+        for (int q = 0; q <= K1S_GROUP; ++q) rs_[q] = k1s_lds32(s_rstart + 4u * (uint32_t)q);
+        uint32_t padsum = 0;
+#pragma unroll
+        for (int q = 0; q < K1S_GROUP; ++q) { pad_[q] = padsum; padsum += (rs_[q + 1] - rs_[q]) & 1u; }
+        const bool overflow = run + padsum > (uint32_t)scap || total_items > 3 * 32 * K1S_IPL;
         if (lane >= g0 && lane < g0 + K1S_GROUP) {
-            const uint32_t a = s_rstart + 4u * (uint32_t)(lane - g0);
-            my_n = k1s_lds32(a + 4u) - k1s_lds32(a);
+            const int q = lane - g0;
+            uint32_t nq = 0;
+#pragma unroll
+            for (int x = 0; x < K1S_GROUP; ++x) if (x == q) nq = rs_[x + 1] - rs_[x];
+            my_n = nq;
             my_slow = my_slow || (have && overflow);
         }
+        // the staging area is free once the engine has read the previous group's records
+        if (pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); pending = false; }
+        __syncwarp();
         if (!overflow) {
-            // per-read output base so that record i of the group goes to tbl[read] + 8 * i
-            if (lane >= g0 && lane < g0 + K1S_GROUP) {
-                const uint32_t a = s_rstart + 4u * (uint32_t)(lane - g0);
-                const unsigned long long ptr = (unsigned long long)(mins + my_moff) - 8ull * k1s_lds32(a);
-                k1s_sts64(s_tbl + 8u * (uint32_t)(lane - g0), ptr);
+            // ---- pass 2: records of every word into the staging area; the K1S_IPL words of a lane are
+            // independent extraction chains inside one loop (one trip count for the warp: the most bits any
+            // word has; a lane whose word has no bit left writes nothing)
+            for (int pz = 0; pz < np_; ++pz) {
+                uint32_t m[K1S_IPL], w0[K1S_IPL], w1[K1S_IPL], w2[K1S_IPL], dst[K1S_IPL], pbase[K1S_IPL];
+                uint32_t most = 0;
+#pragma unroll
+                for (int t = 0; t < K1S_IPL; ++t) {
+                    m[t] = cw[pz][t] < 0 ? 0u : mw[pz][t];
+                    const int q = qw[pz][t], c = cw[pz][t] < 0 ? 0 : cw[pz][t];
+                    uint32_t padq = 0;
+#pragma unroll
+                    for (int x = 0; x < K1S_GROUP; ++x) if (x == q) padq = pad_[x];
+                    const uint32_t a_st = s_wreg + (uint32_t)(g0 + q) * rsb + 8u * (uint32_t)c;      // stream words 2c, 2c+1, 2c+2
+                    w0[t] = k1s_lds32(a_st); w1[t] = k1s_lds32(a_st + 4u); w2[t] = k1s_lds32(a_st + 8u);
+                    dst[t] = s_stage + 8u * (ow[pz][t] + padq);
+                    pbase[t] = 32u * (uint32_t)c;
+                    most = max(most, (uint32_t)__popc(m[t]));
+                }
+                most = __reduce_max_sync(NGSID_FULL_MASK, most);
+                for (uint32_t so = 0; so < 8u * most; so += 8u) {
+#pragma unroll
+                    for (int t = 0; t < K1S_IPL; ++t) {
+                        const uint32_t x = k1s_clz(m[t]);
+                        if (m[t] != 0u) {
+                            const uint32_t hi = x < 16u ? w0[t] : w1[t], lo = x < 16u ? w1[t] : w2[t];
+                            const uint32_t code = k1s_fsl(lo, hi, 2u * x) >> kshift;
+                            k1s_sts64(dst[t] + so, ((unsigned long long)(pbase[t] + x) << 32) | code);
+                        }
+                        m[t] &= k1s_fsr(0x7fffffffu, 0u, x);      // clears bit 31 - x (the bits above it are 0)
+                    }
+                }
             }
             __syncwarp();
-            // flat over the group's records: staged u16 = read-in-group << 13 | position
-            const uint32_t s_greg = s_wreg + (uint32_t)g0 * rsb;
-#pragma unroll 2
-            for (uint32_t i0 = 0; i0 < run; i0 += 32) {
-                const uint32_t i = i0 + (uint32_t)lane;
-                if (i < run) {
-                    const uint32_t v = k1s_lds16(s_stage + 2u * i);
-                    const uint32_t qi = v >> 13;
-                    const uint32_t a = s_greg + qi * rsb + ((v >> 2) & 0x7fcu);      // word (v & 0x1fff) / 16
-                    const uint32_t x = k1s_fsl(k1s_lds32(a + 4u), k1s_lds32(a), v << 1);   // shift 2 * (pos & 15)
-                    const unsigned long long ptr = k1s_lds64(s_tbl + 8u * qi) + 8ull * i;
-                    k1s_stg64(ptr, x >> kshift, v & 0x1fffu);
-                }
+            // ---- one bulk store per read, issued by the read's lane (16-byte multiples: an odd count copies one
+            // stale record more into the slack of the read's slots; nmin says how many are valid)
+            if (lane >= g0 && lane < g0 + K1S_GROUP && have && ok && my_n > 0) {
+                const int q = lane - g0;
+                uint32_t first = 0;
+#pragma unroll
+                for (int x = 0; x < K1S_GROUP; ++x) if (x == q) first = rs_[x] + pad_[x];
+                const uint32_t bytes = ((my_n + 1u) & ~1u) * 8u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"((unsigned long long)(mins + my_moff)), "r"(s_stage + 8u * first), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                pending = true;
             }
         }
         __syncwarp();
     }
+    if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (my_slow) slow_list[atomicAdd(slow_n, 1)] = (int32_t)r;
     else if (have) {
         nmin[r] = my_n;
