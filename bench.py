@@ -45,6 +45,11 @@ CONFIGS = {
            "name": "BASELINE.json configs[1] (cluster-only; consensus leg = configs[2])"},
     "c3": {"reads_per_gpu": 125000, "species": 50, "abundance_ratio": 0.005, "max_seqs": 200, "racon_iter": 3,
            "name": "BASELINE.json configs[3] (cluster + consensus)"},
+    # configs[4] shape per GPU (5 M reads on 8 GPUs = 625 k per GPU; the default here is a bounded 200 k):
+    # mixed-length 500-2000 bp PacBio-profile reads, --isoseq parameters k=15 w=50 (NGSpeciesID:264-269)
+    "c4": {"reads_per_gpu": 200000, "species": 10, "abundance_ratio": 0.02, "max_seqs": 100, "racon_iter": 3,
+           "k": 15, "w": 50, "profile": "pacbio", "len": (1900, 2000), "per_read_len": (500, 2000),
+           "name": "BASELINE.json configs[4] shape (PacBio profile, k=15 w=50, cluster + consensus)"},
 }
 
 
@@ -79,17 +84,19 @@ def vector_scores(qual, offsets, k, block=20000):
     return out
 
 
-def make_workload(n_reads, seed, cache=True, n_species=10, with_templates=False):
-    """n_reads synthetic ONT reads that pass the reference's quality filter, in score order.
+def make_workload(n_reads, seed, cache=True, n_species=10, with_templates=False, k=K, profile="ont", length=(700, 800),
+                  per_read_len=None):
+    """n_reads synthetic reads that pass the reference's quality filter, in score order.
     Returns (seq u8, qual u8, offsets i64, accessions list[str]) [+ templates list[str]]."""
-    path = "/tmp/ngsid_bench_%d_%d_s%d.npz" % (n_reads, seed, n_species)
+    path = "/tmp/ngsid_bench_%d_%d_s%d_%s_k%d.npz" % (n_reads, seed, n_species, profile, k)
     if cache and os.path.exists(path):
         z = np.load(path, allow_pickle=False)
         out = (z["seq"], z["qual"], z["offsets"], [a.decode() for a in z["acc"]])
         return out + ([t.decode() for t in z["templates"]],) if with_templates else out
     from ngspeciesid_b200.synth import simulate_reads
     gen = int(n_reads * 1.12) + 64
-    rs = simulate_reads(gen, n_species=n_species, len_lo=700, len_hi=800, seed=seed)
+    rs = simulate_reads(gen, n_species=n_species, len_lo=length[0], len_hi=length[1], seed=seed, profile=profile,
+                        per_read_len=per_read_len)
     lens = rs.lengths()
     # quality filter of the sort stage (mean uncapped error probability, Q > 7)
     pu = 10.0 ** (-(rs.qual.astype(np.float64) - 33.0) / 10.0)
@@ -98,7 +105,7 @@ def make_workload(n_reads, seed, cache=True, n_species=10, with_templates=False)
     ok = np.nonzero(-10.0 * np.log10(mean_err) > 7.0)[0][:n_reads]
     if len(ok) < n_reads:
         raise RuntimeError("synthetic pool too small")
-    score = vector_scores(rs.qual, rs.offsets, K)[ok]
+    score = vector_scores(rs.qual, rs.offsets, k)[ok]
     order = ok[np.argsort(-score, kind="stable")]
     score_sorted = np.sort(-score, kind="stable") * -1.0
     new_off = np.zeros(n_reads + 1, dtype=np.int64)
@@ -280,14 +287,21 @@ def _measure(args, cfg, env):
     torch, dist, E, M = env["torch"], env["dist"], env["E"], env["M"]
     rank, world, local, p_emp, max_gap = env["rank"], env["world"], env["local"], env["p_emp"], env["max_gap"]
     eng, mg, ce, pe = env["engines"]
+    K, W = cfg.get("k", 13), cfg.get("w", 20)            # shadow the module defaults for this workload
+    if (K, W) != (13, 20):
+        from ngspeciesid_b200.modules import p_minimizers_shared
+        p_emp = p_minimizers_shared.p_emp_for(K, W)
+        max_gap = E.max_gap_table(p_emp, 0.1)
+    wl = dict(n_species=cfg["species"], k=K, profile=cfg.get("profile", "ont"), length=cfg.get("len", (700, 800)),
+              per_read_len=cfg.get("per_read_len"))
     n_total = cfg["reads_per_gpu"] * world
     seed = args.seed + world - 1
     if world > 1:
         # rank 0 generates (or finds) the pool and leaves it in the cache; the others load it
         if rank == 0:
-            make_workload(n_total, seed, n_species=cfg["species"])
+            make_workload(n_total, seed, **wl)
         dist.barrier()
-    seq, qual, offsets, acc, templates = make_workload(n_total, seed, n_species=cfg["species"], with_templates=True)
+    seq, qual, offsets, acc, templates = make_workload(n_total, seed, with_templates=True, **wl)
 
     # --t N semantics: N consecutive batches of the score-sorted list by cumulative nucleotides
     bounds = batch_bounds(np.diff(offsets), world)
@@ -476,7 +490,7 @@ def _measure(args, cfg, env):
                 traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"]); traffic_src = tj["source"]
         except Exception:
             pass
-        result["roofline"] = {"kernel": "k1_stream_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        result["roofline"] = {"kernel": "k1_stream_kernel" if (W - K + 1 == 8 and K <= 13) else "k1_minimizers_kernel (generic, warp per read)", "bound": "hbm", "achieved": achieved, "peak": peak,
                               "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                               "traffic_source": traffic_src, "algorithmic_bytes_per_launch": int(alg_bytes),
                               "bound_note": "reported against HBM as BASELINE asks; the kernel is ALU-issue bound (DESIGN.md 4.0/4.1)",
@@ -504,8 +518,10 @@ def _measure(args, cfg, env):
 
 
 def workload_config(cfg, world):
-    return {"workload": "%s: %d synthetic 750 bp ONT-error reads per GPU (%d in total), %d species, k=13 w=20, --t %d semantics"
-                        % (cfg["name"], cfg["reads_per_gpu"], cfg["reads_per_gpu"] * world, cfg["species"], world),
+    shape = "750 bp ONT-error" if cfg.get("profile", "ont") == "ont" else "500-2000 bp PacBio-profile"
+    return {"workload": "%s: %d synthetic %s reads per GPU (%d in total), %d species, k=%d w=%d, --t %d semantics"
+                        % (cfg["name"], cfg["reads_per_gpu"], shape, cfg["reads_per_gpu"] * world, cfg["species"],
+                           cfg.get("k", 13), cfg.get("w", 20), world),
             "reads_per_gpu": cfg["reads_per_gpu"], "total_reads": cfg["reads_per_gpu"] * world, "species": cfg["species"],
             "l2": "inputs_exceed_l2 (ASCII + packed reads + minimizer records = %.0f MB per GPU)"
                   % (cfg["reads_per_gpu"] * (750 * 2.25 + 119 * 8) / 1e6)}
@@ -611,7 +627,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="auto", choices=["auto", "c1", "c3"])
+    ap.add_argument("--config", default="auto", choices=["auto", "c1", "c3", "c4"])
     ap.add_argument("--reads", type=int, default=0, help="reads per GPU (default: the configuration's)")
     ap.add_argument("--seed", type=int, default=1002)
     ap.add_argument("--tile", type=int, default=0)

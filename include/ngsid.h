@@ -51,7 +51,7 @@ int ngsid_sync(ngsid_ctx *ctx);
 float ngsid_phase_ms(ngsid_ctx *ctx, int which);
 /* Tuning / test switches. option 1 selects the K1 kernel: 0 (default) the stream kernel for
  * w-k+1 == 8, k <= 13 and the generic warp-per-read kernel otherwise; 1 the generic kernel for
- * every (k, w); 2 the older thread-per-read ring kernel instead of the stream kernel.
+ * every (k, w).
  * option 2: value != 0 selects the trace-free payload variant of K4.
  * option 3 selects the shape of the K4 DP kernel: 0 (default) per launch by the number of pairs,
  * 1 always one warp per pair, 2 always one thread block per pair (pipelined strips).

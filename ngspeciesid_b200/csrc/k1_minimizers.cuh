@@ -178,250 +178,6 @@ k1_minimizers_kernel(const uint32_t *__restrict__ packed, const int64_t *__restr
 
 
 // ---------------------------------------------------------------------------------------------
-// K1 fast path (w - k + 1 == 8, k <= 13): one THREAD per read, all state in registers.
-//   * 4 bases at a time go through a 1024-entry shared-memory table (previous base, packed byte)
-//     -> (kept bases, count): homopolymer compression without a per-base branch;
-//   * kept bases queue up in a 64-bit FIFO; every 8 of them form a block: rolling 2k-bit code per
-//     slot, key = code << 4 | slot-in-block, and the sliding minimum over 8 k-mers is
-//     min(suffix minimum of the previous block, prefix minimum of this block) (van Herk /
-//     Gil-Werman), branch-free, leftmost on ties because the slot index sits in the low key bits;
-//   * a minimizer is recorded whenever the window minimum changes; records go to a per-thread
-//     ring in shared memory and leave for HBM in rows of 8 records = 64 bytes (two full sectors),
-//     eight rows per warp-wide store, so DRAM sees whole sectors instead of scattered 8-byte stores;
-//   * the loop is block-centric and warp-uniform: every iteration each lane refills its FIFO
-//     (cheap, variable) and runs exactly one block step (expensive, always useful).
-// Reads whose compressed length is < w (reference quirk, one truncated-window minimizer) are
-// appended to `slow_list` and finished by k1_minimizers_kernel.
-#define K1F_INF 0xffffffffu
-#define K1F_THREADS 128
-#define K1F_RING 16                 // records per thread ring
-#define K1F_RSTRIDE 17              // ring stride in records (padding against bank conflicts)
-#define K1F_ROW 8                   // records per flushed row (64 bytes = two full sectors)
-
-struct K1FastState {
-    uint32_t suf[9];
-    uint32_t code;
-    int base;          // slot index of the first slot of the next block
-    uint32_t last_key; // key of the last recorded minimizer in the frame of the current block
-    uint32_t n_out;
-};
-
-// One block of 8 compressed bases. Records (key, block base) pairs into the thread's ring.
-template <bool PARTIAL>
-__device__ __forceinline__ void k1_fast_block(K1FastState &S, uint32_t ch, int nvalid, int k, int w,
-                                              uint32_t kmask, uint2 *__restrict__ ring)
-{
-    uint32_t key[8];
-    uint32_t pm = K1F_INF;
-    const bool warm = S.base + 7 < w - 1;          // no complete window ends in this block
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const uint32_t b = (ch >> (14 - 2 * t)) & 3u;
-        S.code = ((S.code << 2) | b) & kmask;
-        const int slot = S.base + t;
-        uint32_t kk = (S.code << 4) | (uint32_t)(8 + t);
-        if (slot < k - 1) kk = K1F_INF;
-        if (PARTIAL && t >= nvalid) kk = K1F_INF;
-        key[t] = kk;
-        pm = min(pm, kk);
-        const uint32_t m = min(S.suf[t + 1], pm);
-        bool emit = (m != S.last_key) && !warm && (slot >= w - 1);
-        if (PARTIAL) emit = emit && (t < nvalid);
-        if (emit) {
-            ring[S.n_out & (K1F_RING - 1)] = make_uint2(m, (uint32_t)S.base);
-            S.n_out++;
-            S.last_key = m;
-        }
-    }
-    uint32_t sm = K1F_INF;
-#pragma unroll
-    for (int t = 7; t >= 0; --t) {
-        sm = min(sm, key[t]);
-        S.suf[t] = sm - 8u;          // becomes "previous block": slot tags 0..7
-    }
-    // the same record seen from the next block's frame; a record from the previous block can no
-    // longer be a window minimum, so it must not compare equal to anything
-    S.last_key = (S.last_key & 8u) ? S.last_key - 8u : (K1F_INF - 1u);
-    S.base += 8;
-}
-
-// Steady-state block (every slot >= w-1): no warm-up tests, k-mer codes by funnel shift out of
-// (previous code : 8 new bases), and the record is stored unconditionally at ring[n_out] -- the
-// index only advances when the window minimum changed, otherwise the next store overwrites it.
-__device__ __forceinline__ void k1_fast_block_steady(K1FastState &S, uint32_t ch, uint32_t kmask,
-                                                     uint2 *__restrict__ ring)
-{
-    const uint32_t lo = (S.code << 16) | ch, hi = S.code >> 16;
-    uint32_t key[8];
-    uint32_t pm = K1F_INF;
-    const uint32_t base = (uint32_t)S.base;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const uint32_t c = __funnelshift_r(lo, hi, 14 - 2 * t) & kmask;
-        const uint32_t kk = (c << 4) | (uint32_t)(8 + t);
-        key[t] = kk;
-        pm = min(pm, kk);
-        const uint32_t m = min(S.suf[t + 1], pm);
-        ring[S.n_out & (K1F_RING - 1)] = make_uint2(m, base);
-        S.n_out += (m != S.last_key) ? 1u : 0u;
-        S.last_key = m;
-    }
-    S.code = lo & kmask;
-    uint32_t sm = K1F_INF;
-#pragma unroll
-    for (int t = 7; t >= 0; --t) {
-        sm = min(sm, key[t]);
-        S.suf[t] = sm - 8u;
-    }
-    S.last_key = (S.last_key & 8u) ? S.last_key - 8u : (K1F_INF - 1u);
-    S.base += 8;
-}
-
-// decode a ring record: key = code << 4 | tag, tag 0..7 = previous block, 8..15 = block at `base`
-__device__ __forceinline__ Minimizer k1_fast_decode(uint2 rec, int k)
-{
-    const int slot = (int)rec.y - 8 + (int)(rec.x & 15u);
-    return make_uint2(rec.x >> 4, (uint32_t)(slot - (k - 1)));
-}
-
-__global__ void __launch_bounds__(K1F_THREADS)
-k1_fast_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict__ woff,
-               const int64_t *__restrict__ off, const int64_t *__restrict__ moff,
-               Minimizer *__restrict__ mins, uint32_t *__restrict__ nmin,
-               uint32_t *__restrict__ lenc, int64_t n_reads, int k, int w,
-               int32_t *__restrict__ slow_list, int32_t *__restrict__ slow_n)
-{
-    __shared__ uint16_t lut[1024];
-    __shared__ uint2 rings[K1F_THREADS * K1F_RSTRIDE];
-    for (int idx = threadIdx.x; idx < 1024; idx += blockDim.x) {
-        uint32_t prev = idx >> 8, byte = idx & 255, bits = 0, cnt = 0;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            uint32_t b = (byte >> (6 - 2 * t)) & 3u;
-            if (b != prev) { bits = (bits << 2) | b; cnt++; }
-            prev = b;
-        }
-        lut[idx] = (uint16_t)((cnt << 8) | bits);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool have = r < n_reads;
-    const int L = have ? (int)(off[r + 1] - off[r]) : 0;
-    const uint2 *pk = reinterpret_cast<const uint2 *>(packed + (have ? woff[r] : 0));
-    Minimizer *out = mins + (have ? moff[r] : 0);
-    uint2 *ring = rings + threadIdx.x * K1F_RSTRIDE;
-    const uint32_t kmask = (1u << (2 * k)) - 1u;
-
-    K1FastState S;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) S.suf[t] = K1F_INF;
-    S.code = 0; S.base = 0; S.last_key = K1F_INF - 1u; S.n_out = 0;
-    uint32_t fifo = 0;                          // <= 16 kept bases, newest in the low bits
-    unsigned long long inbuf = 0;
-    int avail = 0, inleft = 0;                  // bytes left in inbuf
-    int bytes_left = L >> 2;                    // whole bytes (4 bases) of input still to consume
-    int next_pair = 0;                          // next uint2 (8 bytes = 32 bases) to load
-    const int n_pairs = (L + 31) >> 5;
-    uint2 ahead = (have && n_pairs > 0) ? __ldg(pk) : make_uint2(0, 0);
-    uint32_t prev = have ? ((ahead.x >> 30) ^ 1u) : 0u, n_fl = 0;
-    bool tail_done = (L == 0);
-    bool active = have;
-
-#define K1F_LOAD_PAIR()                                                              \
-    do {                                                                             \
-        inbuf = ((unsigned long long)ahead.x << 32) | ahead.y;                       \
-        inleft = 8;                                                                  \
-        ++next_pair;                                                                 \
-        if (next_pair < n_pairs) ahead = __ldg(pk + next_pair);                      \
-    } while (0)
-#define K1F_LUT_STEP()                                                               \
-    do {                                                                             \
-        if (inleft == 0) K1F_LOAD_PAIR();                                            \
-        const uint32_t byte_ = (uint32_t)(inbuf >> 56);                              \
-        inbuf <<= 8; --inleft; --bytes_left;                                         \
-        const uint32_t e_ = lut[(prev << 8) | byte_];                                \
-        const uint32_t c_ = e_ >> 8;                                                 \
-        fifo = (fifo << (2 * c_)) | (e_ & 255u);                                     \
-        avail += (int)c_;                                                            \
-        prev = byte_ & 3u;                                                           \
-    } while (0)
-
-    while (__any_sync(NGSID_FULL_MASK, active)) {
-        if (active) {
-            // ---- refill: three straight-line table steps cover the average demand (8 kept bases per
-            // block ~ 2.7 input bytes); the loop behind them only runs after long homopolymers
-#pragma unroll
-            for (int st = 0; st < 3; ++st)
-                if (avail <= 12 && bytes_left > 0) K1F_LUT_STEP();
-            while (avail < 8 && bytes_left > 0) K1F_LUT_STEP();
-            if (avail < 8 && !tail_done) {
-                const int rem = L & 3;          // the last 0..3 bases sit in the next byte
-                if (rem) {
-                    if (inleft == 0) K1F_LOAD_PAIR();
-                    uint32_t byte = (uint32_t)(inbuf >> 56);
-                    for (int t = 0; t < rem; ++t) {
-                        const uint32_t b = (byte >> 6) & 3u;
-                        byte <<= 2;
-                        if (b != prev) { fifo = (fifo << 2) | b; avail++; }
-                        prev = b;
-                    }
-                }
-                tail_done = true;
-            }
-            if (avail >= 8) {
-                const uint32_t ch = (fifo >> (2 * (avail - 8))) & 0xffffu;
-                avail -= 8;
-                if (S.base >= w) k1_fast_block_steady(S, ch, kmask, ring);
-                else k1_fast_block<false>(S, ch, 8, k, w, kmask, ring);
-            } else {
-                if (avail > 0) {                // input exhausted: last partial block
-                    const uint32_t ch = (fifo << (2 * (8 - avail))) & 0xffffu;
-                    const int nv = avail;
-                    avail = 0;
-                    k1_fast_block<true>(S, ch, nv, k, w, kmask, ring);
-                    S.base += nv - 8;            // base now equals the compressed length
-                }
-                active = false;
-            }
-        }
-        // ---- flush full rows of 8 records; eight rows per round, 4 lanes x 16 bytes per row
-        uint32_t fm = __ballot_sync(NGSID_FULL_MASK, have && (S.n_out - n_fl) >= K1F_ROW);
-        while (fm) {
-            // each group of 4 lanes serves the first of its own lanes that has a full row
-            const uint32_t gm = (fm >> (lane & ~3)) & 15u;
-            const int leader = gm ? ((lane & ~3) + __ffs(gm) - 1) : -1;
-            const bool is_leader = (leader == lane);
-            fm = __ballot_sync(NGSID_FULL_MASK, ((fm >> lane) & 1u) && !is_leader);
-            const int src = leader >= 0 ? leader : 0;
-            const uint32_t fl = __shfl_sync(NGSID_FULL_MASK, n_fl, src);
-            const unsigned long long op = __shfl_sync(NGSID_FULL_MASK, (unsigned long long)out, src);
-            if (leader >= 0) {
-                const int e = (lane & 3) * 2;
-                const uint2 *rp = rings + (threadIdx.x - lane + leader) * K1F_RSTRIDE + ((fl + e) & (K1F_RING - 1));
-                const Minimizer a = k1_fast_decode(rp[0], k), b = k1_fast_decode(rp[1], k);
-                reinterpret_cast<uint4 *>(reinterpret_cast<Minimizer *>(op) + fl)[lane & 3] = make_uint4(a.x, a.y, b.x, b.y);
-            }
-            if (is_leader) n_fl += K1F_ROW;
-        }
-    }
-#undef K1F_LUT_STEP
-#undef K1F_LOAD_PAIR
-    if (!have) return;
-    const int Lc = S.base;
-    if (Lc < w) {
-        // compressed read shorter than w (or than k): the generic kernel reproduces the quirk
-        int i = atomicAdd(slow_n, 1);
-        slow_list[i] = (int32_t)r;
-        return;
-    }
-    // leftover records (< 16): written by the owning thread
-    for (uint32_t i = n_fl; i < S.n_out; ++i) out[i] = k1_fast_decode(ring[i & (K1F_RING - 1)], k);
-    nmin[r] = S.n_out;
-    lenc[r] = (uint32_t)Lc;
-}
-
-// ---------------------------------------------------------------------------------------------
 // K0: quality statistics. Reference: modules/cluster.py:273-292 (per homopolymer run keep the
 // quality char of lowest error probability; error rate = sum(count(c)*p(c))/len over the
 // compressed qualities) and cluster.py:185-188 (same sum over the raw qualities / len(seq)).

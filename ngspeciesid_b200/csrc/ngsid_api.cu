@@ -63,8 +63,8 @@ extern "C" int ngsid_set_option(ngsid_ctx *ctx, int option, int value)
 {
     if (!ctx) return NGSID_EINVAL;
     if (option == 1) {
-        if (value < 0 || value > 2) return fail(ctx, NGSID_EINVAL, "option 1 takes 0, 1 or 2");
-        ctx->k1_variant = value == 0 ? 2 : value == 1 ? 0 : 1;
+        if (value < 0 || value > 1) return fail(ctx, NGSID_EINVAL, "option 1 takes 0 or 1");
+        ctx->k1_variant = value == 0 ? 2 : 0;
         ctx->have_min = false;
         return NGSID_OK;
     }
@@ -265,30 +265,24 @@ static int k1_launch_generic(ngsid_ctx *ctx, const int32_t *list, const int32_t 
 
 static int k1_launch(ngsid_ctx *ctx)
 {
-    const bool fast = (ctx->w - ctx->k + 1 == 8) && ctx->k <= 13 && ctx->k >= 2 && ctx->k1_variant != 0;
+    // stream kernel (thread per read for compression + window minima, warp per 32 reads for the output) for
+    // windows of 8 k-mers, k <= 13, as long as its per-thread regions fit; the generic warp-per-read kernel
+    // for every other (k, w) and for the reads the stream kernel hands over (short, or poorly compressing)
+    const K1SGeom g = k1s_geometry(ctx->max_len, ctx->k);
+    const size_t smem = k1s_smem_bytes(g);
+    const bool fast = (ctx->w - ctx->k + 1 == 8) && ctx->k <= 13 && ctx->k >= 2 && ctx->k1_variant != 0 &&
+                      smem <= K1S_SMEM_LIMIT;
     if (!fast) return k1_launch_generic(ctx, nullptr, nullptr, ctx->n_reads);
-    // fast path + hand-over list for reads with a short compressed length
     CUDA_TRY(ctx, ctx->d_newslots.ensure((size_t)(ctx->n_reads + 16) * 4));
     int32_t *slow_n = ctx->d_newslots.as<int32_t>();
     int32_t *slow_list = slow_n + 4;
     CUDA_TRY(ctx, cudaMemsetAsync(slow_n, 0, 16, ctx->stream));
-    const K1SGeom g = k1s_geometry(ctx->max_len, ctx->k);
-    const size_t smem = k1s_smem_bytes(g);
-    if (ctx->k1_variant == 2 && smem <= K1S_SMEM_LIMIT && g.n_it_max + 2 <= 255) {   // staged positions are 13 bits
-        // stream kernel: thread per read for compression + window minima, warp per 32 reads for output
-        CUDA_TRY(ctx, cudaFuncSetAttribute(k1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int blocks = (int)((ctx->n_reads + K1S_THREADS - 1) / K1S_THREADS);
-        k1_stream_kernel<<<blocks, K1S_THREADS, smem, ctx->stream>>>(
-            ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
-            ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
-            ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, g.sw, g.bw, g.rs, g.scap, slow_list, slow_n);
-    } else {
-        int blocks = (int)((ctx->n_reads + 127) / 128);
-        k1_fast_kernel<<<blocks, 128, 0, ctx->stream>>>(
-            ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
-            ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
-            ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, slow_list, slow_n);
-    }
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k1_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (int)((ctx->n_reads + K1S_THREADS - 1) / K1S_THREADS);
+    k1_stream_kernel<<<blocks, K1S_THREADS, smem, ctx->stream>>>(
+        ctx->d_packed.as<uint32_t>(), ctx->d_woff.as<int64_t>(), ctx->d_off.as<int64_t>(),
+        ctx->d_moff.as<int64_t>(), ctx->d_mins.as<Minimizer>(), ctx->d_nmin.as<uint32_t>(),
+        ctx->d_lenc.as<uint32_t>(), ctx->n_reads, ctx->k, ctx->w, g.sw, g.bw, g.rs, g.scap, slow_list, slow_n);
     KERNEL_CHECK(ctx);
     return k1_launch_generic(ctx, slow_list, slow_n, std::min<int64_t>(ctx->n_reads, 4096));
 }

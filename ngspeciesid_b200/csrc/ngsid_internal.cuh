@@ -85,7 +85,7 @@ struct ngsid_ctx {
     int k4_shape = 0;                 // 0: choose per launch, 1: always one warp per pair, 2: always one block per pair
     int k4_tb = 0;                    // option 4: traceback 0 per launch by the number of pairs, 1 warp per pair, 2 thread per pair
     bool use_payload_k4 = false;      // option 2: the trace-free payload kernel instead of DP + traceback
-    int k1_variant = 2;               // 2: stream kernel (default), 1: thread-per-read ring kernel, 0: generic warp-per-read kernel for every (k,w)
+    int k1_variant = 2;               // 2: stream kernel where it applies (default), 0: generic warp-per-read kernel for every (k,w)
     std::vector<int64_t> h_moff;      // n+1 offsets into d_mins (slack CSR: capacity per read)
     std::vector<uint32_t> h_nmin;     // mirror of d_nmin (filled lazily)
     bool h_nmin_valid = false;
