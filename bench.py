@@ -486,7 +486,7 @@ def _measure(args, cfg, env):
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))
-            if int(tj["reads_per_launch"]) == len(blens):
+            if int(tj["reads_per_launch"]) == len(blens) and (W - K + 1 == 8 and K <= 13):
                 traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"]); traffic_src = tj["source"]
         except Exception:
             pass
