@@ -14,10 +14,9 @@
 //                              8 windows), and the result is ONE BIT per minimizer position in a
 //                              per-read bitmap (a minimizer record is fully determined by its
 //                              position), so no compare/branch/store happens per window.
-//   phase C  thread per read   two bitmap words per round -> records (leading-zero extraction, code re-read
-//            + warp flush      from the stream) staged flat in the warp's shared-memory area, each record
-//                              carrying the array slot it belongs to; the warp then stores the staged
-//                              records of the round, 32 consecutive ones per instruction.
+//   phase C  warp per 32 reads bitmap words -> ordered minimizer positions (popcount + warp scan +
+//                              leading-zero extraction) staged in shared memory, then records
+//                              (code, position) leave for HBM as consecutive 8-byte stores per read.
 // All loops run to warp-uniform trip counts; lanes past the end of their read compute garbage in
 // their own shared-memory region, and a per-read fix-up recomputes the last 7 windows exactly.
 // Reads whose compressed length is < w + 8 (including the reference's "shorter than w" quirk) are
@@ -51,8 +50,10 @@ __device__ __forceinline__ uint32_t k1s_min(uint32_t a, uint32_t b) { return min
 #endif
 
 #define K1S_THREADS 128
-#define K1S_SLOT_BIAS 2048u         // phase C: bias of the slot field of a staged record (>= staging capacity)
-#define K1S_BLOCK_SMEM 57344        // dynamic shared memory per block that still lets four blocks share an SM
+#define K1S_GROUP 4                 // reads per extraction group in phase C
+#define K1S_WARP_EXTRA 32           // per warp: read starts of a group (K1S_GROUP + 1 words), 16-byte multiple
+#define K1S_SLOTS 9                 // straight-line extraction slots per bitmap word
+#define K1S_IPL 3                   // bitmap words per lane and extraction pass
 #define K1S_SMEM_LIMIT (160 * 1024)  // above this the read set goes to the ring / generic kernels
 
 #ifdef K1S_HOST
@@ -86,7 +87,7 @@ uint32_t k1s_lut_entry(uint32_t idx)
 struct K1SGeom {
     int n_it_max;      // steps of 32 k-mers the longest possible read needs
     int sw, bw, rs;    // stream words, bitmap words, region stride
-    int scap;          // staged records per warp and round of phase C (8 bytes each)
+    int scap;          // staged records per extraction group (8 bytes each, even); overflow -> generic kernel
 };
 static inline K1SGeom k1s_geometry(int max_len, int k)
 {
@@ -100,19 +101,18 @@ static inline K1SGeom k1s_geometry(int max_len, int k)
     g.bw = g.n_it_max + 2;
     g.rs = g.sw + g.bw;
     if ((g.rs & 1) == 0) g.rs++;
-    // phase C stages the records of one round (64 k-mer positions of each of a warp's 32 reads, ~450 records
-    // on sequencing reads, 2048 at most) per warp; a round that does not fit is flushed in segments of lanes.
-    // 512 slots, or whatever four resident blocks per SM leave (up to 1024).
-    g.scap = 512;
-    const long fixed = 1024 * 4 + ((long)K1S_THREADS * g.rs * 4 + 15) / 16 * 16;
-    const long room = ((long)K1S_BLOCK_SMEM - fixed) / (K1S_THREADS / 32) / 8;
-    if (room > g.scap) g.scap = (int)(room > 1024 ? 1024 : room);
+    // records of a group are staged in shared memory before they leave as one bulk store per read.
+    // Expected density is ~0.22 minimizers per k-mer of the ACTUAL read (regions are sized for the longest
+    // read at 85 % compression); 0.195 per k-mer slot of the region keeps four blocks per SM at 800 bases
+    // and leaves ~3 sigma of headroom; a group that does not fit goes to the generic kernel.
+    g.scap = ((K1S_GROUP * g.n_it_max * 32 * 39 / 200) / 2) * 2;
+    if (g.scap < 128) g.scap = 128;
     return g;
 }
 static inline size_t k1s_smem_bytes(const K1SGeom &g)
 {
     // table | regions | per warp: staging + read starts
-    return 1024 * 4 + ((size_t)K1S_THREADS * g.rs * 4 + 15) / 16 * 16 + (size_t)(K1S_THREADS / 32) * ((size_t)g.scap * 8);
+    return 1024 * 4 + ((size_t)K1S_THREADS * g.rs * 4 + 15) / 16 * 16 + (size_t)(K1S_THREADS / 32) * ((size_t)g.scap * 8 + K1S_WARP_EXTRA);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -384,83 +384,138 @@ k1_stream_kernel(const uint32_t *__restrict__ packed, const int64_t *__restrict_
     }
     __syncwarp();
 
-    // ---- phase C: bitmaps -> records.
-    // Thread per read again: in a round every lane takes two bitmap words (64 k-mer positions) of ITS read and
-    // extracts their set bits as two independent chains (leading-zero count, k-mer code re-read from the stream
-    // words the lane holds in registers). A warp scan of the popcounts gives every lane a range of the warp's
-    // staging area, so the records of a round are staged flat: read after read, each read's records consecutive.
-    // A staged record is 8 bytes {code, position | slot << 12}: `slot` is the index in the minimizer array
-    // (relative to the warp's first read) where flat record 0 of the round would land if it belonged to this
-    // read, so the flush needs no search: lane t stores flat record f = t + 32 i to slot(f) + f. Consecutive
-    // lanes store consecutive records of the same read (a read has ~14 records per round), i.e. the stores of a
-    // warp instruction fall into a handful of 32-byte sectors.
-    // One warp instruction serves 32 reads in the extraction (like phases A and B) and 32 records in the flush.
+    // ---- phase C: bitmaps -> records, K1S_GROUP reads at a time.
+    // One warp instruction here serves 32 bitmap words of a few reads (phases A and B serve 32 reads), so this
+    // part is written against the instruction count. A lane takes K1S_IPL consecutive bitmap words, a warp scan
+    // of their popcounts gives every word the index of its first record, and the lane writes its records
+    // (k-mer code re-read from the compressed stream, position) straight into the group's staging area in
+    // shared memory, read after read (each read starts on a 16-byte boundary). The staged records of a read
+    // then leave as ONE bulk copy shared -> global issued by the read's own lane (cp.async.bulk, the TMA
+    // engine does the coalescing); the wait for the engine's reads of the staging area sits behind the next
+    // group's popcount scan.
     const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(k1s_smem);
-    const uint32_t s_st = s_base + 4096u + (uint32_t)threadIdx.x * ((uint32_t)rs * 4u);         // this thread's region
-    const uint32_t s_bm = s_st + (uint32_t)sw * 4u;
-    const uint32_t s_stage = s_base + 4096u + (((uint32_t)K1S_THREADS * (uint32_t)rs * 4u + 15u) & ~15u) + (uint32_t)wid * (8u * (uint32_t)scap);
+    const uint32_t rsb = (uint32_t)rs * 4u;
+    const uint32_t s_wreg = s_base + 4096u + (uint32_t)(wid * 32) * rsb;          // this warp's 32 regions
+    const uint32_t s_stage = s_base + 4096u + (((uint32_t)K1S_THREADS * rsb + 15u) & ~15u) + (uint32_t)wid * (8u * (uint32_t)scap + K1S_WARP_EXTRA);
+    const uint32_t s_rstart = s_stage + 8u * (uint32_t)scap;
+    const uint32_t bm_off = (uint32_t)sw * 4u;
     const int kshift = 32 - 2 * k;
-    const long long moff0 = __shfl_sync(NGSID_FULL_MASK, my_moff, 0);                            // reads of a warp are consecutive
-    Minimizer *const wbase = mins + moff0 - K1S_SLOT_BIAS;
-    const uint32_t myslot = (uint32_t)(my_moff - moff0) + K1S_SLOT_BIAS;                         // (have ? .. : unused)
-    uint32_t cnt = 0;                                                                             // records of my read so far
-    for (int j = 0; j < n_it; j += 2) {
-        uint32_t m0 = k1s_lds32(s_bm + 4u * (uint32_t)j);
-        uint32_t m1 = (j + 1 < n_it) ? k1s_lds32(s_bm + 4u * (uint32_t)j + 4u) : 0u;
-        const uint32_t p0 = (uint32_t)__popc(m0), p1 = (uint32_t)__popc(m1), n = p0 + p1;
-        uint32_t incl = n;
+    const int total_items = K1S_GROUP * n_it;
+    const int q_l = (K1S_IPL * lane) / n_it, c_l = (K1S_IPL * lane) % n_it;        // first item of this lane in a pass
+    const int dq = (32 * K1S_IPL) / n_it, dc = (32 * K1S_IPL) % n_it;              // advance per pass
+    uint32_t my_n = 0;
+    bool my_slow = have && !ok;
+    bool pending = false;                                                          // bulk copies of the previous group in flight
+    for (int g0 = 0; g0 < 32; g0 += K1S_GROUP) {
+        if (!__any_sync(NGSID_FULL_MASK, have && lane >= g0)) break;
+        // ---- pass 1: popcounts -> index of every word's first record, read starts
+        uint32_t mw[3][K1S_IPL], ow[3][K1S_IPL];                                   // up to 3 passes of 96 words (n_it <= 72)
+        int qw[3][K1S_IPL], cw[3][K1S_IPL];
+        uint32_t run = 0;
+        int qa = q_l, ca = c_l;
+        int np_ = 0;
+        for (int f0 = 0; f0 < total_items && np_ < 3; f0 += 32 * K1S_IPL, ++np_) {
+            int q = qa, c = ca;
+            uint32_t n = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(NGSID_FULL_MASK, incl, d);
-            if (lane >= d) incl += v;
+            for (int t = 0; t < K1S_IPL; ++t) {
+                const bool v = f0 + K1S_IPL * lane + t < total_items;
+                mw[np_][t] = v ? k1s_lds32(s_wreg + (uint32_t)(g0 + q) * rsb + bm_off + 4u * (uint32_t)c) : 0u;
+                qw[np_][t] = q; cw[np_][t] = v ? c : -1;
+                n += (uint32_t)__popc(mw[np_][t]);
+                if (++c >= n_it) { c = 0; ++q; }
+            }
+            uint32_t incl = n;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(NGSID_FULL_MASK, incl, d);
+                if (lane >= d) incl += v;
+            }
+            uint32_t o = run + incl - n;
+#pragma unroll
+            for (int t = 0; t < K1S_IPL; ++t) {
+                ow[np_][t] = o;
+                if (cw[np_][t] == 0) k1s_sts32(s_rstart + 4u * (uint32_t)qw[np_][t], o);
+                o += (uint32_t)__popc(mw[np_][t]);
+            }
+            run += __shfl_sync(NGSID_FULL_MASK, incl, 31);
+            ca += dc; qa += dq;
+            if (ca >= n_it) { ca -= n_it; ++qa; }
         }
-        const uint32_t a_w = s_st + 8u * (uint32_t)j;                                             // stream words 2j .. 2j + 4
-        const uint32_t w0 = k1s_lds32(a_w), w1 = k1s_lds32(a_w + 4u), w2 = k1s_lds32(a_w + 8u);
-        const uint32_t w3 = k1s_lds32(a_w + 12u), w4 = k1s_lds32(a_w + 16u);
-        // the records of a round normally fit the staging area at once; if not, the lanes go in segments
-        uint32_t base = 0;
-        int lo = 0;
-        do {
-            const bool fits = lane >= lo && incl - base <= (uint32_t)scap;                        // a prefix of the lanes >= lo
-            const int hi = lo + __popc(__ballot_sync(NGSID_FULL_MASK, fits));
-            const uint32_t tot = __shfl_sync(NGSID_FULL_MASK, incl, hi - 1) - base;
-            const bool act = lane >= lo && lane < hi;
-            uint32_t a0 = act ? m0 : 0u, a1 = act ? m1 : 0u;
-            const uint32_t E = incl - n - base;                                                   // first flat record of this lane
-            const uint32_t most = __reduce_max_sync(NGSID_FULL_MASK, act ? max(p0, p1) : 0u);
-            const uint32_t d0 = s_stage + 8u * E, d1 = d0 + 8u * p0;
-            const uint32_t yb0 = ((myslot + cnt - E) << 12) + 32u * (uint32_t)j, yb1 = yb0 + 32u;
-            for (uint32_t so = 0; so < 8u * most; so += 8u) {
-                {
-                    const uint32_t x = k1s_clz(a0);
-                    const uint32_t hi_ = x < 16u ? w0 : w1, lo_ = x < 16u ? w1 : w2;
-                    const uint32_t code = k1s_fsl(lo_, hi_, 2u * x) >> kshift;
-                    if (a0 != 0u) k1s_sts64(d0 + so, ((unsigned long long)(yb0 + x) << 32) | code);
-                    a0 &= k1s_fsr(0x7fffffffu, 0u, x);                                            // clears bit 31 - x (the bits above it are 0)
+        if (lane == 0) k1s_sts32(s_rstart + 4u * K1S_GROUP, run);
+        __syncwarp();
+        // per read of the group: first record (flat) and padding so that every read starts on 16 bytes
+        uint32_t rs_[K1S_GROUP + 1], pad_[K1S_GROUP];
+#pragma unroll
+        for (int q = 0; q <= K1S_GROUP; ++q) rs_[q] = k1s_lds32(s_rstart + 4u * (uint32_t)q);
+        uint32_t padsum = 0;
+#pragma unroll
+        for (int q = 0; q < K1S_GROUP; ++q) { pad_[q] = padsum; padsum += (rs_[q + 1] - rs_[q]) & 1u; }
+        const bool overflow = run + padsum > (uint32_t)scap || total_items > 3 * 32 * K1S_IPL;
+        if (lane >= g0 && lane < g0 + K1S_GROUP) {
+            const int q = lane - g0;
+            uint32_t nq = 0;
+#pragma unroll
+            for (int x = 0; x < K1S_GROUP; ++x) if (x == q) nq = rs_[x + 1] - rs_[x];
+            my_n = nq;
+            my_slow = my_slow || (have && overflow);
+        }
+        // the staging area is free once the engine has read the previous group's records
+        if (pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); pending = false; }
+        __syncwarp();
+        if (!overflow) {
+            // ---- pass 2: records of every word into the staging area; the K1S_IPL words of a lane are
+            // independent extraction chains inside one loop (one trip count for the warp: the most bits any
+            // word has; a lane whose word has no bit left writes nothing)
+            for (int pz = 0; pz < np_; ++pz) {
+                uint32_t m[K1S_IPL], w0[K1S_IPL], w1[K1S_IPL], w2[K1S_IPL], dst[K1S_IPL], pbase[K1S_IPL];
+                uint32_t most = 0;
+#pragma unroll
+                for (int t = 0; t < K1S_IPL; ++t) {
+                    m[t] = cw[pz][t] < 0 ? 0u : mw[pz][t];
+                    const int q = qw[pz][t], c = cw[pz][t] < 0 ? 0 : cw[pz][t];
+                    uint32_t padq = 0;
+#pragma unroll
+                    for (int x = 0; x < K1S_GROUP; ++x) if (x == q) padq = pad_[x];
+                    const uint32_t a_st = s_wreg + (uint32_t)(g0 + q) * rsb + 8u * (uint32_t)c;      // stream words 2c, 2c+1, 2c+2
+                    w0[t] = k1s_lds32(a_st); w1[t] = k1s_lds32(a_st + 4u); w2[t] = k1s_lds32(a_st + 8u);
+                    dst[t] = s_stage + 8u * (ow[pz][t] + padq);
+                    pbase[t] = 32u * (uint32_t)c;
+                    most = max(most, (uint32_t)__popc(m[t]));
                 }
-                {
-                    const uint32_t x = k1s_clz(a1);
-                    const uint32_t hi_ = x < 16u ? w2 : w3, lo_ = x < 16u ? w3 : w4;
-                    const uint32_t code = k1s_fsl(lo_, hi_, 2u * x) >> kshift;
-                    if (a1 != 0u) k1s_sts64(d1 + so, ((unsigned long long)(yb1 + x) << 32) | code);
-                    a1 &= k1s_fsr(0x7fffffffu, 0u, x);
+                most = __reduce_max_sync(NGSID_FULL_MASK, most);
+                for (uint32_t so = 0; so < 8u * most; so += 8u) {
+#pragma unroll
+                    for (int t = 0; t < K1S_IPL; ++t) {
+                        const uint32_t x = k1s_clz(m[t]);
+                        if (m[t] != 0u) {
+                            const uint32_t hi = x < 16u ? w0[t] : w1[t], lo = x < 16u ? w1[t] : w2[t];
+                            const uint32_t code = k1s_fsl(lo, hi, 2u * x) >> kshift;
+                            k1s_sts64(dst[t] + so, ((unsigned long long)(pbase[t] + x) << 32) | code);
+                        }
+                        m[t] &= k1s_fsr(0x7fffffffu, 0u, x);      // clears bit 31 - x (the bits above it are 0)
+                    }
                 }
             }
             __syncwarp();
-            // ---- flush: flat record f -> wbase[slot + f]
-            for (uint32_t f = (uint32_t)lane; f < tot; f += 32u) {
-                const unsigned long long v = k1s_lds64(s_stage + 8u * f);
-                const uint32_t y = (uint32_t)(v >> 32);
-                k1s_stg64((unsigned long long)(wbase + ((y >> 12) + f)), (uint32_t)v, y & 0xfffu);
+            // ---- one bulk store per read, issued by the read's lane (16-byte multiples: an odd count copies one
+            // stale record more into the slack of the read's slots; nmin says how many are valid)
+            if (lane >= g0 && lane < g0 + K1S_GROUP && have && ok && my_n > 0) {
+                const int q = lane - g0;
+                uint32_t first = 0;
+#pragma unroll
+                for (int x = 0; x < K1S_GROUP; ++x) if (x == q) first = rs_[x] + pad_[x];
+                const uint32_t bytes = ((my_n + 1u) & ~1u) * 8u;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"((unsigned long long)(mins + my_moff)), "r"(s_stage + 8u * first), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                pending = true;
             }
-            __syncwarp();
-            if (act) cnt += n;
-            base += tot;
-            lo = hi;
-        } while (lo < 32);
+        }
+        __syncwarp();
     }
-    const uint32_t my_n = cnt;
-    const bool my_slow = have && !ok;
+    if (pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     if (my_slow) slow_list[atomicAdd(slow_n, 1)] = (int32_t)r;
     else if (have) {
         nmin[r] = my_n;

@@ -270,11 +270,8 @@ static int k1_launch(ngsid_ctx *ctx)
     // for every other (k, w) and for the reads the stream kernel hands over (short, or poorly compressing)
     const K1SGeom g = k1s_geometry(ctx->max_len, ctx->k);
     const size_t smem = k1s_smem_bytes(g);
-    // (a staged record of its phase C holds the position in 12 bits and a minimizer slot relative to the
-    // warp's first read in 20)
     const bool fast = (ctx->w - ctx->k + 1 == 8) && ctx->k <= 13 && ctx->k >= 2 && ctx->k1_variant != 0 &&
-                      smem <= K1S_SMEM_LIMIT && g.n_it_max * 32 <= 4096 &&
-                      32ll * (ctx->max_len + 8) + 2 * K1S_SLOT_BIAS < (1ll << 20);
+                      smem <= K1S_SMEM_LIMIT;
     if (!fast) return k1_launch_generic(ctx, nullptr, nullptr, ctx->n_reads);
     CUDA_TRY(ctx, ctx->d_newslots.ensure((size_t)(ctx->n_reads + 16) * 4));
     int32_t *slow_n = ctx->d_newslots.as<int32_t>();
