@@ -1064,7 +1064,9 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     const int tmax = params->tile_reads > 0 ? params->tile_reads : 65536;
     const int tgrow = getenv("NGSID_TILE_GROWTH") ? std::max(2, atoi(getenv("NGSID_TILE_GROWTH"))) : 8;
     const int tfirst = getenv("NGSID_TILE_FIRST") ? std::max(1, atoi(getenv("NGSID_TILE_FIRST"))) : 32;
-    int T = std::min(tfirst, tmax);
+    // a pass that starts from a table (a merge round of the --t N path, modules/parallelize.py:153-217) mostly
+    // maps its reads onto that table: no reason to start with a small tile
+    int T = std::min(n_init > 0 ? std::max(tfirst, 256) : tfirst, tmax);
     int pos = 0;
     std::vector<int32_t> U, h_list;
     while (pos < n) {
