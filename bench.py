@@ -262,7 +262,7 @@ def run_ours(args):
                engines=(eng, mg, ce, pe))
     cfg = pick_config(args, world)
     result = _measure(args, cfg, env)
-    if world >= 8 and args.config == "auto" and not args.no_north_star:
+    if (world >= 8 or args.force_north_star) and args.config == "auto" and not args.no_north_star:
         # the north-star run itself: BASELINE.json configs[3], cluster + consensus end to end on the same ranks
         import copy
         a3 = copy.copy(args)
@@ -417,6 +417,8 @@ def _measure(args, cfg, env):
         centers, info = pipe.consensus(cfg["abundance_ratio"], cfg["max_seqs"], cfg["racon_iter"])     # warm-up
         barrier()
         pipe.phase = {}
+        for e in (ce, pe):
+            e.__dict__.pop("poa_acc", None)
         csteps = max(1, min(args.steps, 2))
         l0 = engines_launches()
         tc = time.perf_counter()
@@ -456,6 +458,22 @@ def _measure(args, cfg, env):
                 "phases": cphase, "gpu_launches": cl,
                 "consensus_lengths": [len(c[2]) for c in centers][:12],
                 "edit_distance_to_nearest_template_per_base": [round(d, 5) for d in dists]}
+            # K5 (partial-order alignment) of rank 0's share: a latency-bound kernel, reported as cells per second and
+            # as time per layer step (one dependency chain of graph rows per job)
+            k5 = {"calls": 0, "jobs": 0, "cells": 0, "layer_steps": 0, "device_ms": 0.0, "host_ms": 0.0, "call_ms": 0.0}
+            for e in (ce, pe):
+                for k_, v_ in e.__dict__.get("poa_acc", {}).items():
+                    k5[k_] += v_
+            if k5["call_ms"] > 0:
+                result["consensus"]["k5_rank0"] = {
+                    "kernel": "k5r_layer_kernel (one launch per layer step over all jobs) + host graph updates",
+                    "bound": "latency: serial chain of graph rows per job, one CTA per job (DESIGN.md 4.3)",
+                    "calls_per_step": k5["calls"] / csteps, "jobs_per_step": k5["jobs"] / csteps,
+                    "dp_cells_per_step": k5["cells"] / csteps, "layer_steps_per_step": k5["layer_steps"] / csteps,
+                    "seconds_in_poa_per_step": k5["call_ms"] / 1e3 / csteps,
+                    "gcups": k5["cells"] / (k5["call_ms"] / 1e3) / 1e9,
+                    "ms_per_layer_step": k5["call_ms"] / max(1, k5["layer_steps"]),
+                    "device_share": k5["device_ms"] / k5["call_ms"], "host_graph_share": k5["host_ms"] / k5["call_ms"]}
         # CPU baseline of the consensus leg: the oracle (restated spoa / racon) on whole clusters, one per core
         if rank == 0 and not args.no_cpu and info["clusters_selected"]:
             result["consensus"]["cpu_baseline"] = consensus_cpu_baseline(pipe, ce, info, cfg, lens_mean)
@@ -639,6 +657,8 @@ def main():
     ap.add_argument("--no-consensus", dest="no_consensus", action="store_true")
     ap.add_argument("--no-modules", dest="no_modules", action="store_true")
     ap.add_argument("--no-north-star", dest="no_north_star", action="store_true", help="N = 8: skip the configs[3] run")
+    ap.add_argument("--force-north-star", dest="force_north_star", action="store_true",
+                    help="run the nested configs[3] workload (125 k reads per GPU) at any N: a dry run of the N = 8 path")
     ap.add_argument("--abundance-ratio", dest="abundance_ratio", type=float, default=None)
     ap.add_argument("--max-seqs", dest="max_seqs", type=int, default=None, help="--max_seqs_for_consensus of the consensus leg")
     ap.add_argument("--racon-iter", dest="racon_iter", type=int, default=None)

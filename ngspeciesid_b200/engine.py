@@ -258,6 +258,12 @@ class Engine(object):
         nodes = np.zeros(n_jobs, dtype=np.int32)
         self._check(self.lib.ngsid_poa_consensus(self.h, ctypes.byref(p), n_jobs, ptr(job_off), ptr(src), ptr(beg), ptr(ln),
                                                  ptr(aux_seq), ptr(aux_off), n_aux, ptr(out), stride, ptr(out_len), ptr(nodes)))
+        # running totals for whoever reports K5 (bench.py): DP cells, layer steps (= the longest job of a call:
+        # a call advances every job one layer per kernel launch), kernel + copy / host graph / whole-call time
+        acc = self.__dict__.setdefault("poa_acc", {"calls": 0, "jobs": 0, "cells": 0, "layer_steps": 0, "device_ms": 0.0, "host_ms": 0.0, "call_ms": 0.0})
+        acc["calls"] += 1; acc["jobs"] += n_jobs; acc["cells"] += self.poa_cells()
+        acc["layer_steps"] += int(np.diff(job_off).max())
+        acc["device_ms"] += self.phase_ms(6); acc["host_ms"] += self.phase_ms(7); acc["call_ms"] += self.phase_ms(8)
         return [out[j, :out_len[j]].tobytes().decode("ascii") for j in range(n_jobs)], nodes
 
     # ---- multi-GPU data plane (NCCL inside the library; a world of one rank without a communicator)
