@@ -30,7 +30,9 @@ extern "C" int ngsid_ctx_create(int device_id, ngsid_ctx **out)
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_id) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->up_ev[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->up_ev[1], cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return NGSID_ECUDA;
     }
@@ -96,9 +98,11 @@ extern "C" void ngsid_ctx_destroy(ngsid_ctx *ctx)
                       &ctx->d_cursor, &ctx->d_slot_read, &ctx->d_slot_pos, &ctx->d_slot_state, &ctx->d_order,
                       &ctx->d_accrank, &ctx->d_dec, &ctx->d_aux, &ctx->d_via, &ctx->d_list, &ctx->d_scratch,
                       &ctx->d_params, &ctx->d_req, &ctx->d_reqn, &ctx->d_acache, &ctx->d_k4cnt, &ctx->d_k4score,
-                      &ctx->d_newslots, &ctx->d_cc_a, &ctx->d_cc_b, &ctx->d_cc_c, &ctx->d_aovf, &ctx->d_aovf_head, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm};
+                      &ctx->d_newslots, &ctx->d_cc_a, &ctx->d_cc_b, &ctx->d_cc_c, &ctx->d_aovf, &ctx->d_aovf_head, &ctx->d_ss_tab, &ctx->d_ss_score, &ctx->d_ss_err, &ctx->d_poa_dir, &ctx->d_poa_arena, &ctx->d_poa_meta, &ctx->d_poa_h, &ctx->d_poa_out, &ctx->d_poa_len, &ctx->d_poa_nodes, &ctx->d_poa_err, &ctx->d_job_off, &ctx->d_lsrc, &ctx->d_lbeg, &ctx->d_llen, &ctx->d_trace, &ctx->d_ends, &ctx->d_auxseq, &ctx->d_aoff, &ctx->d_win, &ctx->d_match, &ctx->d_cols, &ctx->d_pa, &ctx->d_pb, &ctx->d_po, &ctx->d_pm,
+                      &ctx->d_cl[0], &ctx->d_cl[1], &ctx->d_cl[2], &ctx->d_cl[3], &ctx->d_cl[4], &ctx->d_cl[5]};
     for (DevBuf *b : bufs) b->release();
     for (int i = 0; i < 6; ++i) for (int j = 0; j < 2; ++j) if (ctx->pev[i][j]) cudaEventDestroy(ctx->pev[i][j]);
+    cudaEventDestroy(ctx->up_ev[0]); cudaEventDestroy(ctx->up_ev[1]);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -197,8 +201,20 @@ extern "C" int ngsid_upload_reads(ngsid_ctx *ctx, const uint8_t *seq, const uint
     int rc = reads_layout(ctx, offsets, n_reads);
     if (rc || n_reads == 0) return rc;
     const size_t nb = (size_t)ctx->total_bases;
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_seq.p, seq, nb, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_qual.p, qual, nb, cudaMemcpyHostToDevice, ctx->stream));
+    // In pieces of 4 MB with at most two of them queued: a copy engine serves its queue in submission order, and
+    // another context on this GPU (a clustering pass running under this upload, multi_gpu.Pipeline.prefetch) has
+    // small latency-critical copies to put into the same queue -- behind 150 MB they would wait 3 ms each.
+    const size_t piece = (size_t)4 << 20;
+    const uint8_t *src[2] = {seq, qual};
+    uint8_t *dst[2] = {ctx->d_seq.as<uint8_t>(), ctx->d_qual.as<uint8_t>()};
+    int q = 0;
+    for (int a = 0; a < 2; ++a)
+        for (size_t o = 0; o < nb; o += piece, ++q) {
+            const size_t len = std::min(piece, nb - o);
+            if (q >= 2) CUDA_TRY(ctx, cudaEventSynchronize(ctx->up_ev[q & 1]));
+            CUDA_TRY(ctx, cudaMemcpyAsync(dst[a] + o, src[a] + o, len, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaEventRecord(ctx->up_ev[q & 1], ctx->stream));
+        }
     return reads_finish(ctx);
 }
 
@@ -958,6 +974,16 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     R.ctx = ctx;
     R.n = n_order;
     memset(&R.st, 0, sizeof(R.st));
+    // the pass borrows its private device buffers from the context and hands them back on every way out
+    struct ClusterLend {
+        ClusterRun &r; ngsid_ctx *c;
+        DevBuf *mine[6];
+        ClusterLend(ClusterRun &r_, ngsid_ctx *c_) : r(r_), c(c_) {
+            DevBuf *m[6] = {&r.keys_alt, &r.heads_alt, &r.d_list2, &r.d_err, &r.d_spec_u, &r.d_spec_mat};
+            for (int i = 0; i < 6; ++i) { mine[i] = m[i]; std::swap(*mine[i], c->d_cl[i]); }
+        }
+        ~ClusterLend() { for (int i = 0; i < 6; ++i) std::swap(*mine[i], c->d_cl[i]); }
+    } lend(R, ctx);
     const int n = (int)n_order;
     const int max_slots = (int)(n_init + n_order) + 1;
     int64_t max_pairs = 0;
@@ -1039,11 +1065,7 @@ extern "C" int ngsid_cluster(ngsid_ctx *ctx, const ngsid_cluster_params *params,
     R.slot_read.reserve(R.slot_cap); R.slot_pos.reserve(R.slot_cap); R.slot_state.reserve(R.slot_cap);
     R.h_dec.assign(n, DEC_NEW);
 
-    auto cleanup = [&](int code) {
-        R.keys_alt.release(); R.heads_alt.release(); R.d_list2.release(); R.d_err.release();
-        R.d_spec_u.release(); R.d_spec_mat.release();
-        return code;
-    };
+    auto cleanup = [&](int code) { return code; };     // the borrowed buffers go back to the context (ClusterLend)
     const bool use_prefetch = getenv("NGSID_NO_PREFETCH") == nullptr;
 
     // ---- initial representatives (merge rounds of modules/parallelize.py:196-215)

@@ -56,6 +56,7 @@ struct ngsid_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t up_ev[2] = {nullptr, nullptr};      // pacing of the upload (two pieces in flight)
     cudaEvent_t pev[6][2] = {};
     bool pev_valid[6] = {false, false, false, false, false, false};
     float phase_acc[6] = {0, 0, 0, 0, 0, 0};
@@ -109,6 +110,8 @@ struct ngsid_ctx {
     int nccl_rank = 0, nccl_nranks = 1;
     DevBuf d_cc_a, d_cc_b, d_cc_c;
     DevBuf d_req, d_reqn, d_acache, d_k4cnt, d_k4score, d_newslots, d_pa, d_pb, d_po, d_pm;
+    DevBuf d_cl[6];                    // buffers a clustering pass borrows (spare table pair, second list, error words, prefetch tables): kept
+                                       // between passes -- cudaMalloc / cudaFree synchronise the whole device, other contexts' streams included
 };
 
 #define CUDA_TRY(ctx, call)                                                                    \

@@ -15,6 +15,7 @@ The functions that only compute plans are pure (tested on the CPU over gloo with
 stand-in engine, tests/test_multi_gpu_gloo.py); `Pipeline` drives Engine objects.
 """
 import struct
+import threading
 import time
 
 import numpy as np
@@ -170,26 +171,78 @@ class Pipeline(object):
     """eng: Engine of this rank's batch; mg / ce / pe: further Engines on the same GPU for the gathered
     representatives, the reads of the draft step and the reads of the polishing step."""
 
-    def __init__(self, eng, mg, ce, pe, rank=0, world=1, k=13, w=20, cluster_kw=None):
+    def __init__(self, eng, mg, ce, pe, rank=0, world=1, k=13, w=20, cluster_kw=None, alt=None):
         self.eng, self.mg, self.ce, self.pe = eng, mg, ce, pe
+        self.alt = alt                      # second batch engine on the same GPU: double-buffered input (prefetch)
         self.rank, self.world, self.k, self.w = rank, world, k, w
         self.kw = dict(cluster_kw or {})
         self.phase = {}
+        self._pf, self._pf_time, self._pf_err = None, 0.0, None
+        self._pf_delay = 0.0                 # seconds into the current pass at which a prefetch starts its transfer
 
     def _tick(self, name, t0):
         self.eng.sync()
         self.phase[name] = self.phase.get(name, 0.0) + (time.perf_counter() - t0)
         return time.perf_counter()
 
+    # ---- double-buffered input -------------------------------------------------------------------
+    def prefetch(self, upload, delay=0.0):
+        """Start moving the NEXT batch in: H2D copy + 2-bit packing of upload = (seq, qual, offsets) on the
+        alternate engine (its own stream), driven by a host thread, so that the transfer runs under the
+        clustering pass of the current batch. `cluster(prefetched=True)` then switches to that engine and runs
+        K1 / K0 there (kernels of a second stream would only get SM slots when the pass's long alignment launch
+        ends, i.e. after the pass: measured 15 ms for 0.7 ms of work). delay: seconds to wait before the
+        transfer starts (cluster(then_prefetch=...) passes the point where its pass enters the bulk phase)."""
+        if self.alt is None or self._pf is not None:
+            raise RuntimeError("prefetch needs an alternate engine and no prefetch in flight")
+        alt = self.alt
+
+        def work():
+            try:
+                # A large H2D transfer delays every small copy and sync of a pass that runs under it (measured:
+                # +3 ms per 150 MB, scripts/prefetch_probe.py, with any copy code). The first third of a pass is its
+                # latency-bound part (small speculation tiles); the rest waits for one long alignment launch. So the
+                # transfer starts once the pass is in that bulk phase.
+                if delay > 0:
+                    time.sleep(delay)
+                t = time.perf_counter()
+                alt.upload(*upload)
+                alt.sync()
+                self._pf_time = time.perf_counter() - t
+            except Exception as exc:            # surfaces in cluster()
+                self._pf_err = exc
+        self._pf = threading.Thread(target=work, daemon=True)
+        self._pf.start()
+
+    def _take_prefetched(self):
+        if self._pf is None:
+            raise RuntimeError("no prefetch in flight")
+        self._pf.join()
+        self._pf = None
+        if self._pf_err is not None:
+            err, self._pf_err = self._pf_err, None
+            raise err
+        self.eng, self.alt = self.alt, self.eng
+        self.phase["upload_prefetched"] = self.phase.get("upload_prefetched", 0.0) + self._pf_time
+
     # ---- clustering ------------------------------------------------------------------------------
-    def cluster(self, max_gap, accs, scores, gid0, n_total, upload=None, tile_reads=0):
+    def cluster(self, max_gap, accs, scores, gid0, n_total, upload=None, tile_reads=0, prefetched=False,
+                then_prefetch=None):
         """accs / scores: accession strings (with score suffix) and scores of the local reads in
         processing order; gid0: global index of the first local read. upload = (seq, qual, offsets)
-        host arrays, or None when the reads are already resident with K1 / K0 results.
+        host arrays, or None when the reads are already resident. prefetched=True: the batch was handed
+        to `prefetch` before (alternate engine, already on the device); then_prefetch = the batch after this one,
+        started right away so that its transfer runs under this pass.
         Returns the final root (global read id) of every local read (-2: skipped by the reference)."""
-        eng, mg = self.eng, self.mg
         t = time.perf_counter()
-        if upload is not None:
+        if prefetched:
+            self._take_prefetched()
+            t = self._tick("wait_prefetch", t)
+            if then_prefetch is not None:
+                self.prefetch(then_prefetch, delay=self._pf_delay)
+            t = self._tick("start_prefetch", t)
+        eng, mg = self.eng, self.mg
+        if upload is not None and not prefetched:
             eng.upload(*upload)
             t = self._tick("upload", t)
         eng.minimizers(self.k, self.w)
@@ -201,15 +254,21 @@ class Pipeline(object):
         assign, via, st = eng.cluster(self.k, self.w, max_gap, np.arange(n, dtype=np.int32), self._acc_rank,
                                       tile_reads=tile_reads, **self.kw)
         self.local_assign, self.local_stats = assign, st
+        t_pass = time.perf_counter() - t
         t = self._tick("cluster_local", t)
+        self._pf_delay = 0.35 * t_pass
         reps = np.nonzero(assign == -1)[0].astype(np.int32)
         rep_of = np.where(assign >= 0, assign, np.arange(n))
         rep_of[assign == -2] = -1
         size0_local = np.bincount(rep_of[rep_of >= 0], minlength=n)[reps]
         # ---- exchange: plans over the host all-gather, representatives device to device
         blob = pack_rep_tags([gid0 + int(r) for r in reps], [scores[r] for r in reps], size0_local, [accs[r] for r in reps])
-        blobs = eng.allgather_bytes(blob)
-        counts = eng.gather_representatives(reps, mg)
+        if self.world > 1:
+            blobs = eng.allgather_bytes(blob)
+            counts = eng.gather_representatives(reps, mg)
+        else:
+            # one rank: there is no merge round, nothing ever reads a gathered copy of the representatives
+            blobs, counts = [blob], np.array([len(reps)], dtype=np.int64)
         t = self._tick("gather_representatives", t)
         gids, gscores, gsizes, gaccs = [], [], [], []
         for b in blobs:
