@@ -59,6 +59,12 @@ float ngsid_phase_ms(ngsid_ctx *ctx, int which);
  * 1 always one warp per pair, 2 always one thread per pair (no window breaking points).         */
 int ngsid_set_option(ngsid_ctx *ctx, int option, int value);
 
+/* Page-locked host memory for the arrays ngsid_upload_reads takes (no context needed): an upload from it runs at
+ * the full PCIe rate and the host layer can fill it in place. The reference has no counterpart: it hands reads over
+ * as Python str (modules/cluster.py:207). */
+int ngsid_pinned_alloc(void **out, int64_t bytes);
+int ngsid_pinned_free(void *p);
+
 /* ---- read upload ---------------------------------------------------------------------------
  * seq / qual: ASCII bases and PHRED+33 qualities of n_reads reads, concatenated; offsets has
  * n_reads+1 entries (offsets[0] == 0). Copies host->device and packs bases 2 bit/base on the device

@@ -14,7 +14,7 @@ EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last
            "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus",
            "ngsid_fastq_parse", "ngsid_nccl_unique_id", "ngsid_nccl_init", "ngsid_nccl_finalize", "ngsid_nccl_share", "ngsid_allgather_bytes",
            "ngsid_allreduce", "ngsid_gather_representatives", "ngsid_exchange_reads", "ngsid_append_revcomp",
-           "ngsid_download_reads", "ngsid_kmer_string", "ngsid_hit_counts"]
+           "ngsid_download_reads", "ngsid_kmer_string", "ngsid_hit_counts", "ngsid_pinned_alloc", "ngsid_pinned_free"]
 
 
 class ClusterParams(ctypes.Structure):
@@ -94,6 +94,8 @@ def load():
     lib.ngsid_append_revcomp.argtypes = [vp]
     lib.ngsid_download_reads.argtypes = [vp, i64, i64, vp, vp, vp]
     lib.ngsid_kmer_string.argtypes = [vp, ctypes.c_uint32, ctypes.c_char_p, i32]
+    lib.ngsid_pinned_alloc.argtypes = [P(vp), i64]
+    lib.ngsid_pinned_free.argtypes = [vp]
     lib.ngsid_hit_counts.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     for name in EXPORTS:
         getattr(lib, name)

@@ -40,6 +40,37 @@ def build_library(force=False, verbose=False):
     return OUT
 
 
+HOSTPACK_SRC = os.path.join(HERE, "csrc", "hostpack.c")
+
+
+def hostpack_path():
+    import sysconfig
+    return os.path.join(HERE, "_hostpack" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_hostpack(force=False):
+    """The CPython helper of the modules/ layer (csrc/hostpack.c: tuples of str -> byte arrays), gcc."""
+    import sysconfig
+    out = hostpack_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(HOSTPACK_SRC):
+        return out
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I", sysconfig.get_paths()["include"],
+           "-o", out, HOSTPACK_SRC]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("gcc failed for _hostpack")
+    return out
+
+
+def load_hostpack():
+    """The _hostpack module, compiled on first use when __graft_entry__.build() has not been run (gcc, 1 s)."""
+    import importlib
+    build_hostpack()
+    return importlib.import_module("ngspeciesid_b200._hostpack")
+
+
 if __name__ == "__main__":
     build_library(force=True, verbose=True)
+    build_hostpack(force=True)
     print(OUT)

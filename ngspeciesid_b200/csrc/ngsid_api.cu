@@ -120,6 +120,18 @@ extern "C" int ngsid_sync(ngsid_ctx *ctx)
     return NGSID_OK;
 }
 
+extern "C" int ngsid_pinned_alloc(void **out, int64_t bytes)
+{
+    if (!out || bytes < 0) return NGSID_EINVAL;
+    *out = nullptr;
+    return cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) == cudaSuccess ? NGSID_OK : NGSID_ECUDA;
+}
+
+extern "C" int ngsid_pinned_free(void *p)
+{
+    return (!p || cudaFreeHost(p) == cudaSuccess) ? NGSID_OK : NGSID_ECUDA;
+}
+
 // ================================================================================ upload + pack
 // Layout of a new read set: host offsets, word offsets of the packed reads, device buffers sized,
 // d_off / d_woff uploaded. The caller then fills d_seq / d_qual (host or peer data) and calls

@@ -62,7 +62,10 @@ def accession_ranks(accessions):
     n = len(accessions)
     if n == 0:
         return np.zeros(0, dtype=np.uint32)
-    arr = np.array([a.encode("utf-8") for a in accessions])
+    try:
+        arr = np.array(accessions, dtype="S")             # ASCII accessions: one pass inside numpy
+    except UnicodeEncodeError:
+        arr = np.array([a.encode("utf-8") for a in accessions])
     order = np.argsort(arr, kind="stable")
     srt = arr[order]
     start = np.ones(n, dtype=bool)
@@ -89,6 +92,11 @@ class Engine(object):
 
     def close(self):
         if getattr(self, "h", None):
+            pinned = self.__dict__.pop("_pinned", None)
+            if pinned is not None:
+                self.h_seq = self.h_qual = None              # views into the page-locked buffers
+                for p_ in pinned[1]:
+                    self.lib.ngsid_pinned_free(p_)
             self.lib.ngsid_ctx_destroy(self.h)
             self.h = None
 
@@ -116,6 +124,28 @@ class Engine(object):
         self.h_seq, self.h_qual = seq, qual
         self._qcs = None
         self._q_done = False
+
+    def pinned_pair(self, nbytes):
+        """Two page-locked uint8 arrays of at least `nbytes` (kept and grown by the engine) for bases and
+        qualities: the host layer packs records into them in place and uploads from them."""
+        cur = self.__dict__.get("_pinned")
+        if cur is None or cur[0] < nbytes:
+            if cur is not None:
+                self.h_seq = self.h_qual = None              # they may be views into the buffers about to go
+                self._pinned = None
+                for p_ in cur[1]:
+                    self.lib.ngsid_pinned_free(p_)
+            cap = int(nbytes + nbytes // 4 + 4096)
+            ptrs = []
+            for _ in range(2):
+                p_ = ctypes.c_void_p()
+                rc = self.lib.ngsid_pinned_alloc(ctypes.byref(p_), cap)
+                if rc != 0 or not p_:
+                    raise NgsidError(rc, "ngsid_pinned_alloc failed")
+                ptrs.append(p_)
+            arrs = [np.ctypeslib.as_array((ctypes.c_uint8 * cap).from_address(p_.value)) for p_ in ptrs]
+            self._pinned = cur = (cap, ptrs, arrs)
+        return cur[2][0], cur[2][1]
 
     def upload_records(self, records):
         """records: iterable of (seq:str, qual:str)."""
@@ -358,6 +388,17 @@ class Engine(object):
                 self._check(n)
             return buf.value.decode("ascii")
         return decode_kmer(code, k)
+
+    def kmer_strings(self, codes, k):
+        """[kmer_string(c, k) for c in codes], the plain 2k-bit codes decoded in one numpy pass."""
+        codes = np.asarray(codes, dtype=np.uint32)
+        special = (codes >> 30) != 0                       # truncated suffix (bit 31) or dictionary entry (bit 30)
+        shifts = np.arange(2 * (k - 1), -1, -2, dtype=np.uint32)
+        letters = np.frombuffer(b"ACGT", dtype=np.uint8)[(codes[:, None] >> shifts[None, :]) & 3]
+        out = [row.tobytes().decode("ascii") for row in letters] if k else [""] * len(codes)
+        for i in np.nonzero(special)[0].tolist():
+            out[i] = self.kmer_string(codes[i], k)
+        return out
 
     def poa_cells(self):
         """DP cells (graph rows x layer bases, summed) of the last poa_consensus call."""

@@ -3,13 +3,18 @@ Drop-in for the reference's modules/cluster.py hot path (ksahlin/NGSpeciesID v0.
 the GPU through libngsid.so. Function names, arguments, mutation of the caller's dicts and return
 values follow the reference (file:line cited per function); there is no CPU fallback.
 """
+import collections
 import itertools
 import logging
 import math
+import operator
 
 import numpy as np
 
 from .. import engine as _engine
+from ..build import load_hostpack
+
+_hostpack = load_hostpack()          # csrc/hostpack.c: tuples of str -> byte arrays (host glue)
 
 
 def _hpol(seq):
@@ -58,19 +63,22 @@ def reads_to_clusters(clusters, representatives, sorted_reads, p_emp_probs, mini
     ({kmer: set(ids)}), returns {new_batch_index: (clusters, representatives,
     minimizer_database, new_batch_index)}."""
     k, w = args.k, args.w
-    prev_b = [r[1] for r in sorted_reads]
+    prev_b = list(map(operator.itemgetter(1), sorted_reads))
     lowest = max(1, min(prev_b or [1]))
 
     # reads whose batch index equals the lowest one are the table's own representatives:
     # only their batch index changes (modules/cluster.py:243-248)
-    todo = []
-    for rec in sorted_reads:
-        rid = rec[0]
-        if rec[1] == lowest:
-            t = representatives[rid]
-            representatives[rid] = t[:1] + (new_batch_index,) + t[2:]
-        else:
-            todo.append(rec)
+    if lowest in prev_b:
+        todo = []
+        for rec in sorted_reads:
+            rid = rec[0]
+            if rec[1] == lowest:
+                t = representatives[rid]
+                representatives[rid] = t[:1] + (new_batch_index,) + t[2:]
+            else:
+                todo.append(rec)
+    else:
+        todo = sorted_reads if isinstance(sorted_reads, list) else list(sorted_reads)
 
     # representatives already in the caller's table
     init_ids = set()
@@ -79,19 +87,19 @@ def reads_to_clusters(clusters, representatives, sorted_reads, p_emp_probs, mini
     init_ids = sorted(init_ids)
 
     if todo:
-        # one upload for the table's representatives (first) and the reads to cluster; everything
-        # per read below is done on arrays, Python objects are touched for survivors and moves only
+        # one upload for the table's representatives (first) and the reads to cluster. Everything per read
+        # below runs inside C or numpy: the two str fields of the records go straight into byte arrays
+        # (_hostpack.pack_fields), Python objects are touched for survivors and in bulk for the moves.
         n_init, n_todo = len(init_ids), len(todo)
-        init_recs = [representatives[rid] for rid in init_ids]
-        seqs = [t[3] for t in init_recs] + [r[3] for r in todo]
-        quals = [t[4] for t in init_recs] + [r[4] for r in todo]
-        accs = [t[2] for t in init_recs] + [r[2] for r in todo]
-        ids = np.array(init_ids + [r[0] for r in todo], dtype=np.int64)
-        offs = np.zeros(len(seqs) + 1, dtype=np.int64)
-        np.cumsum(np.fromiter(map(len, seqs), np.int64, len(seqs)), out=offs[1:])
+        recs = [representatives[rid] for rid in init_ids] + todo if n_init else todo
         eng = _engine.get_engine(getattr(args, "device", 0))
-        eng.upload(np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8),
-                   np.frombuffer("".join(quals).encode("ascii"), dtype=np.uint8), offs)
+        total = _hostpack.measure_fields(recs, 3)
+        h_seq, h_qual = eng.pinned_pair(total)                       # page-locked, owned by the engine
+        offs = np.frombuffer(_hostpack.pack_fields_into(recs, 3, 4, h_seq.ctypes.data, h_qual.ctypes.data, total),
+                             dtype=np.int64)
+        ids = np.fromiter(map(operator.itemgetter(0), recs), np.int64, len(recs))
+        accs = list(map(operator.itemgetter(2), recs))
+        eng.upload(h_seq[:total], h_qual[:total], offs)
         eng.minimizers(k, w)
         eng.quality_stats()
         max_gap = _engine.max_gap_table(p_emp_probs, args.min_prob_no_hits)
@@ -114,19 +122,28 @@ def reads_to_clusters(clusters, representatives, sorted_reads, p_emp_probs, mini
                 err_c, _eu, _bk = eng.get_quality_stats(li, li + 1)
                 representatives[rid] = (rid, new_batch_index, acc, seq, qual, score, float(err_c[0]), _hpol(seq))
             _lc, _cnt, kmer, _pos = eng.get_minimizers(li, li + 1)
-            for c in kmer:
-                m = eng.kmer_string(c, k)
+            for m in eng.kmer_strings(kmer, k):
                 s = minimizer_database.get(m)
                 if s is None:
                     minimizer_database[m] = s = set()
                 s.add(rid)
-        # assigned reads join their representative in processing order (cluster.py:338-345)
+        # assigned reads join their representative in processing order (cluster.py:338-345): per winner, the
+        # accession lists of its reads are concatenated in that order; the loops run inside C (map / chain)
         moved = np.nonzero(assign >= 0)[0]
-        winners = ids[assign[moved]].tolist()
-        for i, winner in zip(moved.tolist(), winners):
-            rid = todo[i][0]
-            clusters[winner].extend(clusters.pop(rid))
-            del representatives[rid]
+        if len(moved):
+            win_local = assign[moved]
+            by_winner = np.argsort(win_local, kind="stable")             # stable: processing order within a winner
+            moved_ids = ids[n_init + moved[by_winner]]
+            win_sorted = win_local[by_winner]
+            cuts = np.nonzero(np.diff(win_sorted))[0] + 1
+            starts = [0] + cuts.tolist() + [len(moved)]
+            moved_list = moved_ids.tolist()
+            pop_cluster = clusters.pop
+            for g in range(len(starts) - 1):
+                group = moved_list[starts[g]:starts[g + 1]]
+                winner = int(ids[win_sorted[starts[g]]])
+                clusters[winner].extend(itertools.chain.from_iterable(map(pop_cluster, group)))
+            collections.deque(map(representatives.__delitem__, moved_list), maxlen=0)
         logging.debug("Total number of reads iterated through:{0}".format(len(sorted_reads)))
         logging.debug("Passed mapping criteria:{0}".format(stats["n_mapped"]))
         logging.debug("Passed alignment criteria in this process:{0}".format(stats["n_aln_passed"]))

@@ -1,6 +1,8 @@
 """Host-side helpers of the product path (no GPU): bucket thresholds, gap table, ranks, batching."""
 import math
 
+import pytest
+
 import numpy as np
 
 from ngspeciesid_b200 import engine
@@ -78,3 +80,46 @@ def test_round_snapshot_files_match_reference(tmp_path):
         parallelize.print_intermediate_results(clusters, reps, SimpleNamespace(outfolder=str(tmp_path)), c["it"])
         for name, text in c["files"].items():
             assert open(os.path.join(str(tmp_path), str(c["it"]), name)).read() == text
+
+
+def test_hostpack_pack_fields_matches_join():
+    """csrc/hostpack.c: tuples of str -> the arrays ngsid_upload_reads takes, the same bytes as join + encode."""
+    import random
+    from ngspeciesid_b200.build import load_hostpack
+    _hostpack = load_hostpack()
+    rng = random.Random(7)
+    recs = []
+    for i in range(500):
+        n = rng.randrange(0, 40)
+        s = "".join(rng.choice("ACGTN") for _ in range(n))
+        rec = (i, 0, "acc_%d" % i, s, "".join(chr(33 + rng.randrange(60)) for _ in range(n)), 1.0)
+        recs.append(rec if i % 3 else list(rec) + [0.1, "x"])          # tuples and lists, 6 and 8 fields
+    a, q, o = _hostpack.pack_fields(recs, 3, 4)
+    off = np.frombuffer(o, dtype=np.int64)
+    assert a == "".join(r[3] for r in recs).encode() and q == "".join(r[4] for r in recs).encode()
+    assert off[0] == 0 and off[-1] == len(a) and list(np.diff(off)) == [len(r[3]) for r in recs]
+    assert _hostpack.pack_fields([], 3, 4)[0] == b""
+    assert _hostpack.measure_fields(recs, 3) == len(a)
+    da, dq = np.zeros(len(a) + 8, dtype=np.uint8), np.zeros(len(a) + 8, dtype=np.uint8)
+    o2 = _hostpack.pack_fields_into(recs, 3, 4, da.ctypes.data, dq.ctypes.data, len(a))
+    assert o2 == o and da[:len(a)].tobytes() == a and dq[:len(a)].tobytes() == q and not da[len(a):].any()
+    with pytest.raises(BufferError):
+        _hostpack.pack_fields_into(recs, 3, 4, da.ctypes.data, dq.ctypes.data, len(a) - 1)
+    for bad, exc in (([(0, "é", "I")], ValueError), ([(0, "AC", "I")], ValueError), ([(0, b"AC", "II")], TypeError),
+                     ([(0, "AC")], IndexError), ([5], TypeError)):
+        with pytest.raises(exc):
+            _hostpack.pack_fields(bad, 1, 2)
+
+
+def test_accession_ranks_ascii_and_unicode_agree_with_python_order():
+    from ngspeciesid_b200 import engine as E
+    accs = ["read_10_3.5", "read_9_3.5", "a", "read_10_3.5", "Z", "é_1", "~"]
+    r = E.accession_ranks(accs)
+    order = sorted(set(accs), key=lambda x: x.encode("utf-8"))
+    for i, a in enumerate(accs):
+        for j, b_ in enumerate(accs):
+            assert (r[i] < r[j]) == (order.index(a) < order.index(b_))
+    r2 = E.accession_ranks(accs[:5])
+    for i in range(5):
+        for j in range(5):
+            assert (r2[i] < r2[j]) == (accs[i] < accs[j])
