@@ -238,6 +238,20 @@ int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t 
                         int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
                         int32_t *out_nodes);
 
+/* The same with racon's treatment of window layers that do not span their window (racon window.cpp
+ * generate_consensus, behind consensus.run_racon, modules/consensus.py:107-126): layer l with
+ * layer_sub_begin[l] >= 0 is aligned only to the sub-graph between the backbone positions
+ * layer_sub_begin[l] .. layer_sub_end[l] (inclusive; the backbone is the job's first layer) -- the nodes
+ * reached from backbone node `end` over in-edges and aligned nodes with id >= `begin` (spoa
+ * Graph::subgraph) -- and then added to the whole graph; -1 = the whole graph. Both arrays NULL =
+ * ngsid_poa_consensus. */
+int ngsid_poa_consensus_sub(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                            const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                            const int32_t *layer_len, const int32_t *layer_sub_begin, const int32_t *layer_sub_end,
+                            const uint8_t *aux_seq, const int64_t *aux_off,
+                            int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                            int32_t *out_nodes);
+
 /* ---- multi-GPU data plane (one process per GPU, NCCL over NVLink / NVSwitch) --------------------
  * Replaces: the exchange of the reference's --t N mode -- modules/parallelize.py:153-187, where the
  * process pool returns (clusters, representatives, minimizer_database) of every batch to the parent

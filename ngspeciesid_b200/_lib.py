@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libngsid.so")
 EXPORTS = ["ngsid_version", "ngsid_ctx_create", "ngsid_ctx_destroy", "ngsid_last_error",
            "ngsid_launch_count", "ngsid_poa_cells", "ngsid_reset_launch_count", "ngsid_sync", "ngsid_phase_ms", "ngsid_set_option", "ngsid_upload_reads",
            "ngsid_minimizers", "ngsid_minimizers_timed", "ngsid_get_minimizers",
-           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus",
+           "ngsid_quality_stats", "ngsid_get_quality_stats", "ngsid_sort_scores", "ngsid_cluster", "ngsid_sg_block_align", "ngsid_sg_align_paths", "ngsid_poa_consensus", "ngsid_poa_consensus_sub",
            "ngsid_fastq_parse", "ngsid_nccl_unique_id", "ngsid_nccl_init", "ngsid_nccl_finalize", "ngsid_nccl_share", "ngsid_allgather_bytes",
            "ngsid_allreduce", "ngsid_gather_representatives", "ngsid_exchange_reads", "ngsid_append_revcomp",
            "ngsid_download_reads", "ngsid_kmer_string", "ngsid_hit_counts", "ngsid_pinned_alloc", "ngsid_pinned_free"]
@@ -82,6 +82,7 @@ def load():
     lib.ngsid_sg_block_align.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, vp]
     lib.ngsid_sg_align_paths.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp, vp, vp]
     lib.ngsid_poa_consensus.argtypes = [vp, P(PoaParams), i64, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
+    lib.ngsid_poa_consensus_sub.argtypes = [vp, P(PoaParams), i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
     lib.ngsid_fastq_parse.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, P(i64)]
     lib.ngsid_nccl_unique_id.argtypes = [vp, i64]
     lib.ngsid_nccl_init.argtypes = [vp, vp, i32, i32]

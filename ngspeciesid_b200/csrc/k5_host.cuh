@@ -30,6 +30,15 @@ struct HostGraph {
     PoaGraph G;
     int Lmax = 1;
     bool init = false;
+    // the rows of the current layer step: the whole graph in its topological order, or the sub-graph a layer
+    // that does not span its window is aligned to (poa_subgraph_view)
+    bool sub = false;
+    int Vs = 0;
+    std::vector<int32_t> v_order, v_rank;
+    std::vector<uint8_t> v_member;
+    const int32_t *row_order() const { return sub ? v_order.data() : G.order; }
+    const int32_t *row_rank() const { return sub ? v_rank.data() : G.rank; }
+    int rows() const { return sub ? Vs : G.V; }
     void alloc(int Vcap, int lmax) {
         const int Ecap = Vcap * 4, Acap = Vcap * 8, Scap = Ecap + Acap + Vcap + 64;
         Lmax = lmax;
@@ -54,26 +63,34 @@ struct HostGraph {
 
 struct Layer { const uint8_t *s; const uint8_t *q; int L; int64_t arena_off; };
 
-// rows of the graph in topological order for the kernel; returns the number of overflow entries
-static int64_t build_rows(const PoaGraph &G, int ring, uint4 *rows, uint2 *plans, int32_t *ovf, bool count_only, int *max_np)
+// rows of the graph (or of the current sub-graph view) in topological order for the kernel; returns the number
+// of overflow entries. In a view, edges from / to nodes outside it do not exist.
+static int64_t build_rows(const HostGraph &hg, int ring, uint4 *rows, uint2 *plans, int32_t *ovf, bool count_only, int *max_np)
 {
+    const PoaGraph &G = hg.G;
+    const int Vr = hg.rows();
+    const int32_t *order = hg.row_order(), *rank = hg.row_rank();
+    const uint8_t *member = hg.sub ? hg.v_member.data() : nullptr;
     int64_t n_ovf = 0;
-    const bool pack16 = G.V + 1 < 65535;
+    const bool pack16 = Vr + 1 < 65535;
     const int inl = pack16 ? K5R_INLINE16 : K5R_INLINE32;
-    for (int r = 0; r < G.V; ++r) {
-        const int v = G.order[r];
+    for (int r = 0; r < Vr; ++r) {
+        const int v = order[r];
         int np = 0;
-        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) ++np;
+        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) if (!member || member[G.e_from[e]]) ++np;
         if (np > *max_np) *max_np = np;
         if (count_only) { if (np > inl) n_ovf += np; continue; }
-        uint32_t f[4] = {(uint32_t)G.letter[v] | ((uint32_t)std::min(np, 255) << 8) | (G.out_head[v] < 0 ? K5R_FLAG_SINK : 0u) |
+        bool sink = true;
+        for (int e = G.out_head[v]; e >= 0 && sink; e = G.e_next_out[e]) if (!member || member[G.e_to[e]]) sink = false;
+        uint32_t f[4] = {(uint32_t)G.letter[v] | ((uint32_t)std::min(np, 255) << 8) | (sink ? K5R_FLAG_SINK : 0u) |
                          (pack16 ? K5R_FLAG_PACK16 : 0u), 0u, 0u, 0u};
         int u = 0;
         if (np > inl) f[1] = (uint32_t)n_ovf;
         // plan of the row for the pipelined loop: previous row, virtual row, two more near rows
         uint32_t chain_u = 255, virt_u = np == 0 ? 0u : 255u, npre = 0, generic = np > K5R_MAXE ? 1u : 0u, py = 0;
-        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e], ++u) {
-            const int p = G.rank[G.e_from[e]] + 1;
+        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) {
+            if (member && !member[G.e_from[e]]) continue;
+            const int p = rank[G.e_from[e]] + 1;
             if (np > inl) ovf[n_ovf + u] = p;
             else if (pack16) f[1 + (u >> 1)] |= (uint32_t)p << ((u & 1) * 16);
             else f[1 + u] = (uint32_t)p;
@@ -82,6 +99,7 @@ static int64_t build_rows(const PoaGraph &G, int ring, uint4 *rows, uint2 *plans
             if (dist == 1) chain_u = (uint32_t)u;
             else if (dist < ring && npre < 2 && u < 255) { py |= ((uint32_t)dist | ((uint32_t)u << 8)) << (16 * npre); ++npre; }
             else generic = 1;
+            ++u;
         }
         if (np > inl) n_ovf += np;
         rows[r] = make_uint4(f[0], f[1], f[2], f[3]);
@@ -115,11 +133,12 @@ static int host_threads(const ngsid_ctx *ctx)
     return std::max(1, std::min(16, (hw > 0 ? hw : 4) / ranks));
 }
 
-extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
-                                   const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
-                                   const int32_t *layer_len, const uint8_t *aux_seq, const int64_t *aux_off,
-                                   int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
-                                   int32_t *out_nodes)
+static int poa_consensus_impl(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                              const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                              const int32_t *layer_len, const int32_t *layer_sub_begin, const int32_t *layer_sub_end,
+                              const uint8_t *aux_seq, const int64_t *aux_off,
+                              int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                              int32_t *out_nodes)
 {
     using namespace k5host;
     if (!ctx || !params || n_jobs < 0) return NGSID_EINVAL;
@@ -206,13 +225,22 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         }
         const int nd = (int)dp_jobs.size();
         if (nd == 0) { ms_host += since(t_h); continue; }
-        // ---- sizes
+        // ---- sizes (a layer with a sub-graph range is aligned to that part of its graph only)
         int Lstep = 1, max_np = 0;
         std::vector<int> np_max((size_t)nd, 0);
 #pragma omp parallel for num_threads(T) schedule(dynamic, 1)
         for (int x = 0; x < nd; ++x) {
             const int j = dp_jobs[x];
-            n_ovf_of[j] = build_rows(graphs[j].G, ring, nullptr, nullptr, nullptr, true, &np_max[x]);
+            const int64_t l = job_off[j] + step;
+            HostGraph &hg = graphs[j];
+            hg.sub = false;
+            if (layer_sub_begin && layer_sub_begin[l] >= 0 && layer_sub_end[l] >= layer_sub_begin[l] && layer_sub_end[l] < hg.G.V) {
+                hg.v_order.resize((size_t)hg.G.V); hg.v_rank.resize((size_t)hg.G.V); hg.v_member.resize((size_t)hg.G.V);
+                hg.Vs = poa_subgraph_view(hg.G, layer_sub_begin[l], layer_sub_end[l], hg.v_member.data(), hg.v_order.data(), hg.v_rank.data());
+                if (hg.Vs < 0) { jerr[j] = hg.G.err ? hg.G.err : 4; hg.Vs = 0; }
+                hg.sub = true;
+            }
+            n_ovf_of[j] = build_rows(hg, ring, nullptr, nullptr, nullptr, true, &np_max[x]);
         }
         desc.assign((size_t)nd, K5RJob());
         int64_t meta_n = 0, ovf_n = 0, mat_n = 0, path_n = 0;
@@ -229,15 +257,16 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
             const int j = dp_jobs[x];
             const int64_t l = job_off[j] + step;
             const PoaGraph &G = graphs[j].G;
+            const int Vr = graphs[j].rows();
             K5RJob &D = desc[x];
-            D.V = G.V; D.L = layer_len[l]; D.mode = params->mode;
+            D.V = Vr; D.L = layer_len[l]; D.mode = params->mode;
             D.match = params->match; D.mismatch = params->mismatch; D.gap = params->gap;
             D.seq_off = lay_off[l];
-            D.meta_off = meta_n; meta_n += G.V;
+            D.meta_off = meta_n; meta_n += Vr;
             D.ovf_off = ovf_n; ovf_n += n_ovf_of[j];
-            D.mat_off = mat_n; mat_n += (int64_t)(G.V + 1) * ld;
-            D.path_off = path_n; path_n += G.V + D.L + 2;
-            total_cells += (int64_t)G.V * D.L;
+            D.mat_off = mat_n; mat_n += (int64_t)(Vr + 1) * ld;
+            D.path_off = path_n; path_n += Vr + D.L + 2;
+            total_cells += (int64_t)Vr * D.L;
             if (max_nodes > 0 && G.V > max_nodes) return fail(ctx, NGSID_EUNSUPPORTED, "POA graph larger than max_nodes");
         }
         // ---- rows of every graph into pinned memory, then to the device
@@ -254,7 +283,7 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
 #pragma omp parallel for num_threads(T) schedule(dynamic, 1)
         for (int x = 0; x < nd; ++x) {
             int dummy = 0;
-            build_rows(graphs[dp_jobs[x]].G, ring, h_rows + desc[x].meta_off, h_plan + desc[x].meta_off, h_ovf + desc[x].ovf_off, false, &dummy);
+            build_rows(graphs[dp_jobs[x]], ring, h_rows + desc[x].meta_off, h_plan + desc[x].meta_off, h_ovf + desc[x].ovf_off, false, &dummy);
         }
         ms_host += since(t_h);
         auto t_d = std::chrono::steady_clock::now();
@@ -305,8 +334,9 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
             if (h_out[x * 16 + 2]) { jerr[j] = h_out[x * 16 + 2]; continue; }
             const int n = h_out[x * 16];
             const int2 *pp = h_path + desc[x].path_off;
+            const int32_t *row_node = graphs[j].row_order();
             for (int t = 0; t < n; ++t) {
-                G.aln_node[t] = pp[t].x > 0 ? G.order[pp[t].x - 1] : -1;
+                G.aln_node[t] = pp[t].x > 0 ? row_node[pp[t].x - 1] : -1;
                 G.aln_pos[t] = pp[t].y;
             }
             const uint8_t *q = layer_src[l] >= 0 ? h_lqual + lay_off[l] : nullptr;
@@ -347,4 +377,26 @@ extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *param
         return fail(ctx, NGSID_EUNSUPPORTED, msg);
     }
     return NGSID_OK;
+}
+
+extern "C" int ngsid_poa_consensus(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                                   const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                                   const int32_t *layer_len, const uint8_t *aux_seq, const int64_t *aux_off,
+                                   int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                                   int32_t *out_nodes)
+{
+    return poa_consensus_impl(ctx, params, n_jobs, job_off, layer_src, layer_begin, layer_len, nullptr, nullptr,
+                              aux_seq, aux_off, n_aux, out_seq, out_stride, out_len, out_nodes);
+}
+
+extern "C" int ngsid_poa_consensus_sub(ngsid_ctx *ctx, const ngsid_poa_params *params, int64_t n_jobs,
+                                       const int64_t *job_off, const int32_t *layer_src, const int32_t *layer_begin,
+                                       const int32_t *layer_len, const int32_t *layer_sub_begin, const int32_t *layer_sub_end,
+                                       const uint8_t *aux_seq, const int64_t *aux_off,
+                                       int64_t n_aux, uint8_t *out_seq, int64_t out_stride, int32_t *out_len,
+                                       int32_t *out_nodes)
+{
+    if ((layer_sub_begin == nullptr) != (layer_sub_end == nullptr)) return NGSID_EINVAL;
+    return poa_consensus_impl(ctx, params, n_jobs, job_off, layer_src, layer_begin, layer_len, layer_sub_begin, layer_sub_end,
+                              aux_seq, aux_off, n_aux, out_seq, out_stride, out_len, out_nodes);
 }

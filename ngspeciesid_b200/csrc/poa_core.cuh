@@ -177,6 +177,60 @@ POA_HD void poa_topo_sort(PoaGraph &G)
     for (int r = 0; r < n; ++r) G.rank[G.order[r]] = r;
 }
 
+// The part of the graph a racon window aligns a layer to when the layer does not span the window (racon
+// window.cpp generate_consensus -> spoa Graph::subgraph(begin, end)): the nodes reached from backbone node
+// `end` by walking in-edges and aligned nodes while the node id stays >= `begin` (the backbone is the first
+// sequence of the graph, so a backbone node's id is its window position), re-sorted by the depth-first
+// rule of poa_topo_sort restricted to them. member[v] = 1 for the nodes of the view, order[0..n) their
+// topological order, rank[v] = position in it (-1 outside). Returns n, or -1 on stack overflow.
+POA_HD int poa_subgraph_view(PoaGraph &G, int begin, int end, uint8_t *member, int32_t *order, int32_t *rank)
+{
+    const int n = G.V;
+    int sp = 0, n_order = 0;
+    for (int i = 0; i < n; ++i) { member[i] = 0; rank[i] = -1; G.mark[i] = 0; G.check[i] = 1; }
+    G.stack[sp++] = end;
+    while (sp > 0) {
+        const int v = G.stack[--sp];
+        if (member[v] || v < begin) continue;
+        for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) { if (sp >= G.Scap) { G.err = 4; return -1; } G.stack[sp++] = G.e_from[e]; }
+        for (int a = G.al_head[v]; a >= 0; a = G.al_next[a]) { if (sp >= G.Scap) { G.err = 4; return -1; } G.stack[sp++] = G.al_node[a]; }
+        member[v] = 1;
+    }
+    for (int i = 0; i < n; ++i) {
+        if (!member[i] || G.mark[i]) continue;
+        G.stack[sp++] = i;
+        while (sp > 0) {
+            const int v = G.stack[sp - 1];
+            bool ok = true;
+            const int mv = G.mark[v];
+            if (mv == 0) {
+                for (int e = G.in_head[v]; e >= 0; e = G.e_next_in[e]) {
+                    const int u = G.e_from[e];
+                    if (member[u] && G.mark[u] != 2) { if (sp >= G.Scap) { G.err = 4; return -1; } G.stack[sp++] = u; ok = false; }
+                }
+                if (G.check[v]) {
+                    for (int a = G.al_head[v]; a >= 0; a = G.al_next[a]) {
+                        const int u = G.al_node[a];
+                        if (member[u] && G.mark[u] != 2) { if (sp >= G.Scap) { G.err = 4; return -1; } G.stack[sp++] = u; G.check[u] = 0; ok = false; }
+                    }
+                }
+            }
+            if (mv != 2) {
+                if (ok) {
+                    G.mark[v] = 2;
+                    if (G.check[v]) {
+                        order[n_order++] = v;
+                        for (int a = G.al_head[v]; a >= 0; a = G.al_next[a]) if (member[G.al_node[a]]) order[n_order++] = G.al_node[a];
+                    }
+                } else G.mark[v] = 1;
+            }
+            if (ok) --sp;
+        }
+    }
+    for (int r = 0; r < n_order; ++r) rank[order[r]] = r;
+    return n_order;
+}
+
 // Traceback over the DP matrix H ((V+1) rows of `ld` ints; row r+1 = node order[r], column j =
 // j sequence bases consumed). Fills aln_node/aln_pos in reverse order; returns the number of pairs.
 POA_HD int poa_traceback(PoaGraph &G, const int32_t *H, size_t ld, const uint8_t *s, int mode,

@@ -264,9 +264,11 @@ class Engine(object):
         return (score, nmatch, ncols, win) if want_windows else (score, nmatch, ncols)
 
     def poa_consensus(self, job_off, layer_src, layer_begin, layer_len, aux=None, mode=0, match=5,
-                      mismatch=-4, gap=-2, trim=False, max_nodes=0):
+                      mismatch=-4, gap=-2, trim=False, max_nodes=0, layer_sub=None):
         """K5: one POA consensus per job. Layers index uploaded reads (>= 0) or aux strings (< 0).
         max_nodes > 0 bounds the graph of a job (an error beyond it); 0 = as large as it gets.
+        layer_sub = (begin, end) arrays: backbone positions a layer is aligned between (racon's sub-graph
+        alignment of layers that do not span their window), -1 = the whole graph.
         Returns (list of consensus strings, node counts)."""
         job_off = as_array(job_off, np.int64)
         src, beg, ln = as_array(layer_src, np.int32), as_array(layer_begin, np.int32), as_array(layer_len, np.int32)
@@ -286,8 +288,16 @@ class Engine(object):
         out = np.zeros((n_jobs, stride), dtype=np.uint8)
         out_len = np.zeros(n_jobs, dtype=np.int32)
         nodes = np.zeros(n_jobs, dtype=np.int32)
-        self._check(self.lib.ngsid_poa_consensus(self.h, ctypes.byref(p), n_jobs, ptr(job_off), ptr(src), ptr(beg), ptr(ln),
-                                                 ptr(aux_seq), ptr(aux_off), n_aux, ptr(out), stride, ptr(out_len), ptr(nodes)))
+        if layer_sub is not None:
+            sb, se = as_array(layer_sub[0], np.int32), as_array(layer_sub[1], np.int32)
+            if len(sb) != len(src) or len(se) != len(src):
+                raise ValueError("layer_sub arrays must have one entry per layer")
+            self._check(self.lib.ngsid_poa_consensus_sub(self.h, ctypes.byref(p), n_jobs, ptr(job_off), ptr(src), ptr(beg), ptr(ln),
+                                                         ptr(sb), ptr(se), ptr(aux_seq), ptr(aux_off), n_aux, ptr(out), stride,
+                                                         ptr(out_len), ptr(nodes)))
+        else:
+            self._check(self.lib.ngsid_poa_consensus(self.h, ctypes.byref(p), n_jobs, ptr(job_off), ptr(src), ptr(beg), ptr(ln),
+                                                     ptr(aux_seq), ptr(aux_off), n_aux, ptr(out), stride, ptr(out_len), ptr(nodes)))
         # running totals for whoever reports K5 (bench.py): DP cells, layer steps (= the longest job of a call:
         # a call advances every job one layer per kernel launch), kernel + copy / host graph / whole-call time
         acc = self.__dict__.setdefault("poa_acc", {"calls": 0, "jobs": 0, "cells": 0, "layer_steps": 0, "device_ms": 0.0, "host_ms": 0.0, "call_ms": 0.0})

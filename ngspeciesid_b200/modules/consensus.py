@@ -100,13 +100,18 @@ def polish_round_batch(eng, targets, read_lists, rc_lists=None, max_nodes=0):
         segc = np.maximum(seg, 1)
         mean_q = (qcs[roff + np.maximum(q1, 0)] - qcs[roff + np.maximum(q0, 0)]) / segc.astype(np.float64)
         ok &= ~(mean_q < 10.0)
+        # a layer that spans the window to within 1 % at both ends is aligned to the whole window graph, a
+        # shorter one to the sub-graph between its first and last backbone position (racon window.cpp)
         off = 0.01 * wlen
         b, e = t0 - ws, t1 - ws - 1
-        ok &= (b < off) & (e > wlen - off)
+        spans = (b < off) & (e > wlen - off)
         rows = np.nonzero(ok)[0]
         if len(rows):
+            sb = np.where(spans[rows], -1, b[rows]).astype(np.int64)
+            se = np.where(spans[rows], -1, e[rows]).astype(np.int64)
             layer_rows.append(np.stack([(-B[rows] - 1).astype(np.int64), np.full(len(rows), w, dtype=np.int64), b[rows].astype(np.int64),
-                                        rows.astype(np.int64), A[rows].astype(np.int64), q0[rows].astype(np.int64), seg[rows]], axis=1))
+                                        rows.astype(np.int64), A[rows].astype(np.int64), q0[rows].astype(np.int64), seg[rows],
+                                        sb, se], axis=1))
     out = []
     if not layer_rows:
         return list(targets)
@@ -117,21 +122,23 @@ def polish_round_batch(eng, targets, read_lists, rc_lists=None, max_nodes=0):
     key = L[:, 0] * 16 + L[:, 1]
     uniq, start, count = np.unique(key, return_index=True, return_counts=True)
     job_off, src, beg, ln, job_key = [0], [], [], [], []
+    sub_b, sub_e = [], []
     for u, s0, c in zip(uniq, start, count):
         if c + 1 < 3:
             continue
         t, w = int(u // 16), int(u % 16)
         ws = w * WINDOW
         wlen = min(WINDOW, len(targets[t]) - ws)
-        src.append(-t - 1); beg.append(ws); ln.append(wlen)
+        src.append(-t - 1); beg.append(ws); ln.append(wlen); sub_b.append(-1); sub_e.append(-1)
         rows = L[s0:s0 + c]
         src.extend(rows[:, 4].tolist()); beg.extend(rows[:, 5].tolist()); ln.extend(rows[:, 6].tolist())
+        sub_b.extend(rows[:, 7].tolist()); sub_e.extend(rows[:, 8].tolist())
         job_off.append(len(src))
         job_key.append((t, w))
     cons = {}
     if job_key:
         res, _nodes = eng.poa_consensus(job_off, src, beg, ln, aux=targets, mode=1, match=3, mismatch=-5, gap=-4,
-                                        trim=True, max_nodes=max_nodes)
+                                        trim=True, max_nodes=max_nodes, layer_sub=(sub_b, sub_e))
         cons = dict(zip(job_key, res))
     for t, tgt in enumerate(targets):
         parts = []

@@ -13,8 +13,9 @@ oracle/poa_oracle.cpp):
                    the target is cut into 500-base windows; a read contributes to a window the
                    stretch between its first and last aligned (=/X) column inside the window
                    (racon's breaking points) when that stretch is at least 2 % of the window, has
-                   mean quality >= 10 and spans the window to within 1 % at both ends (racon aligns
-                   shorter layers to a sub-graph; they are dropped here and in the CUDA path);
+                   mean quality >= 10; a layer that spans the window to within 1 % at both ends is
+                   aligned to the whole window graph, a shorter one to the sub-graph between its first
+                   and last backbone position (spoa Graph::subgraph, oracle/poa_oracle.cpp);
                    window consensus = global POA (3 / -5 / -4) of backbone (weight 0) + layers
                    sorted by start, coverage-trimmed; windows with < 3 sequences keep the backbone;
                    the polished target is the concatenation.
@@ -38,6 +39,12 @@ def _lib():
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
                                                 ctypes.POINTER(ctypes.c_int)]
+        lib.oracle_poa_consensus_sub.restype = ctypes.c_int
+        lib.oracle_poa_consensus_sub.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p),
+                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                                 ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int,
+                                                 ctypes.POINTER(ctypes.c_int)]
         lib.oracle_sg_align.restype = ctypes.c_int
         lib.oracle_sg_align.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -50,7 +57,9 @@ def _lib():
 ORDER_MODE = 0        # 0 = spoa's re-sort (reference-faithful), 1 = path insertion (the kernel's order)
 
 
-def poa_consensus(seqs, quals=None, mode=0, match=5, mismatch=-4, gap=-2, trim=False, order_mode=None):
+def poa_consensus(seqs, quals=None, mode=0, match=5, mismatch=-4, gap=-2, trim=False, order_mode=None, sub=None):
+    """sub: optional [(begin, end) or None per sequence]: backbone positions of the first sequence that the
+    sequence is aligned between (racon's sub-graph alignment); None / missing = the whole graph."""
     n = len(seqs)
     arr = (ctypes.c_char_p * n)(*[s.encode() for s in seqs])
     qarr = None
@@ -60,7 +69,13 @@ def poa_consensus(seqs, quals=None, mode=0, match=5, mismatch=-4, gap=-2, trim=F
     out = ctypes.create_string_buffer(cap)
     nn = ctypes.c_int(0)
     om = ORDER_MODE if order_mode is None else order_mode
-    r = _lib().oracle_poa_consensus_ex(arr, qarr, n, mode, match, mismatch, gap, 1 if trim else 0, om, out, cap, ctypes.byref(nn))
+    if sub is not None:
+        sb = (ctypes.c_int * n)(*[(-1 if x is None else int(x[0])) for x in sub])
+        se = (ctypes.c_int * n)(*[(-1 if x is None else int(x[1])) for x in sub])
+        r = _lib().oracle_poa_consensus_sub(arr, qarr, n, mode, match, mismatch, gap, 1 if trim else 0, om, sb, se, out, cap,
+                                            ctypes.byref(nn))
+    else:
+        r = _lib().oracle_poa_consensus_ex(arr, qarr, n, mode, match, mismatch, gap, 1 if trim else 0, om, out, cap, ctypes.byref(nn))
     if r < 0:
         raise MemoryError("oracle_poa_consensus")
     return out.value.decode()
@@ -134,9 +149,8 @@ def racon_round(target, reads, window=WINDOW, both_strands=False):
                 continue
             off = 0.01 * wlen
             b, e = t0 - ws, t1 - ws - 1
-            if not (b < off and e > wlen - off):
-                continue
-            layers[wi].append((b, seq[q0:q1], sq))
+            spans = b < off and e > wlen - off
+            layers[wi].append((b, seq[q0:q1], sq, None if spans else (b, e)))
     out = []
     for wi in range(n_win):
         ws = wi * window
@@ -147,7 +161,7 @@ def racon_round(target, reads, window=WINDOW, both_strands=False):
             continue
         seqs = [backbone] + [l[1] for l in ls]
         quals = [""] + [l[2] for l in ls]
-        out.append(poa_consensus(seqs, quals, mode=1, match=3, mismatch=-5, gap=-4, trim=True))
+        out.append(poa_consensus(seqs, quals, mode=1, match=3, mismatch=-5, gap=-4, trim=True, sub=[None] + [l[3] for l in ls]))
     return "".join(out)
 
 

@@ -102,10 +102,80 @@ struct Graph {
 
 struct Pair { int node, pos; };
 
-// mode 0 = local, 1 = global (both with linear gap g)
-static std::vector<Pair> align(const Graph &G, const char *s, int L, int mode, int m, int x, int g)
+// The part of the graph a racon window aligns a layer to when the layer does not span the window
+// (racon window.cpp generate_consensus -> spoa Graph::subgraph(begin, end) of the vendored spoa 3.x): the
+// nodes reached from backbone node `end` by walking in-edges and aligned nodes while the node id stays
+// >= `begin` (backbone nodes carry their window position as id: the backbone is the first sequence of
+// the graph), with the edges and aligned links between them, re-sorted by the same depth-first rule.
+struct View {
+    std::vector<int> order, rank;            // rank of a non-member: -1
+    std::vector<uint8_t> member;
+};
+
+static View subgraph_view(const Graph &G, int begin, int end)
 {
-    const int V = (int)G.letter.size();
+    const int n = (int)G.letter.size();
+    View W;
+    W.member.assign(n, 0);
+    std::vector<int> st;
+    st.push_back(end);
+    while (!st.empty()) {
+        const int v = st.back(); st.pop_back();
+        if (W.member[v] || v < begin) continue;
+        for (int e : G.in[v]) st.push_back(G.edges[e].from);
+        for (int a : G.aligned[v]) st.push_back(a);
+        W.member[v] = 1;
+    }
+    // Graph::topo_sort restricted to the members (ids ascending = the sub-graph's own node order)
+    std::vector<uint8_t> mark(n, 0), check(n, 1);
+    for (int i = 0; i < n; ++i) {
+        if (!W.member[i] || mark[i]) continue;
+        st.push_back(i);
+        while (!st.empty()) {
+            const int v = st.back();
+            bool ok = true;
+            if (mark[v] != 2) {
+                for (int e : G.in[v]) { const int u = G.edges[e].from; if (W.member[u] && mark[u] != 2) { st.push_back(u); ok = false; } }
+                if (check[v]) for (int a : G.aligned[v]) if (W.member[a] && mark[a] != 2) { st.push_back(a); check[a] = 0; ok = false; }
+                if (ok) {
+                    mark[v] = 2;
+                    if (check[v]) { W.order.push_back(v); for (int a : G.aligned[v]) if (W.member[a]) W.order.push_back(a); }
+                } else mark[v] = 1;
+            }
+            if (ok) st.pop_back();
+        }
+    }
+    W.rank.assign(n, -1);
+    for (size_t r = 0; r < W.order.size(); ++r) W.rank[W.order[r]] = (int)r;
+    return W;
+}
+
+static View whole_view(const Graph &G)
+{
+    View W;
+    W.order = G.order; W.rank = G.rank;
+    W.member.assign(G.letter.size(), 1);
+    return W;
+}
+
+// mode 0 = local, 1 = global (both with linear gap g); W: the nodes taking part, in topological order
+static std::vector<Pair> align(const Graph &G0, const View &W, const char *s, int L, int mode, int m, int x, int g)
+{
+    // the DP below reads the graph through `G`: in / out lists restricted to the members of the view
+    struct Sub {
+        const Graph &g; const View &w;
+        std::vector<std::vector<int>> in;        // member in-edges (edge ids, insertion order) per node
+        std::vector<uint8_t> has_out;
+        const std::vector<char> &letter; const std::vector<Edge> &edges; const std::vector<int> &order, &rank;
+        Sub(const Graph &g_, const View &w_) : g(g_), w(w_), letter(g_.letter), edges(g_.edges), order(w_.order), rank(w_.rank) {
+            in.resize(g.letter.size()); has_out.assign(g.letter.size(), 0);
+            for (int v : w.order) {
+                for (int e : g.in[v]) if (w.member[g.edges[e].from]) in[v].push_back(e);
+                for (int e : g.out[v]) if (w.member[g.edges[e].to]) has_out[v] = 1;
+            }
+        }
+    } G(G0, W);
+    const int V = (int)W.order.size();
     std::vector<Pair> aln;
     if (V == 0 || L == 0) return aln;
     const int NEG = INT_MIN / 4;
@@ -143,7 +213,7 @@ static std::vector<Pair> align(const Graph &G, const char *s, int L, int mode, i
             }
             at(row, j) = h;
         }
-        if (mode == 1 && G.out[v].empty()) {
+        if (mode == 1 && !G.has_out[v]) {
             if (at(row, L) > best) { best = at(row, L); bi = row; bj = L; }
         }
     }
@@ -336,8 +406,20 @@ int oracle_poa_consensus(const char **seqs, const char **quals, int n, int mode,
 /* order_mode 0: spoa's topological re-sort after every sequence (reference-faithful);
  * order_mode 1: "path insertion" order maintenance (what the CUDA kernel does; any topological
  * order gives a valid POA, the two differ only in tie-breaks between equal scores). */
+int oracle_poa_consensus_sub(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                             int trim, int order_mode, const int *sub_b, const int *sub_e, char *out, int cap, int *n_nodes_out);
+
 int oracle_poa_consensus_ex(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
                             int trim, int order_mode, char *out, int cap, int *n_nodes_out)
+{
+    return oracle_poa_consensus_sub(seqs, quals, n, mode, m, x, g, trim, order_mode, nullptr, nullptr, out, cap, n_nodes_out);
+}
+
+/* sub_b / sub_e (or NULL): per sequence the backbone positions [sub_b, sub_e] of the first sequence the
+ * sequence covers; >= 0 aligns it to that sub-graph only (racon's treatment of layers that do not span
+ * their window), -1 to the whole graph. */
+int oracle_poa_consensus_sub(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                             int trim, int order_mode, const int *sub_b, const int *sub_e, char *out, int cap, int *n_nodes_out)
 {
     Graph G;
     G.order_mode = order_mode;
@@ -350,7 +432,10 @@ int oracle_poa_consensus_ex(const char **seqs, const char **quals, int n, int mo
             for (int t = 0; t < L; ++t) wt[t] = (t < ql) ? (int)quals[i][t] - 33 : 0;
         }
         std::vector<Pair> aln;
-        if (!G.letter.empty()) aln = align(G, seqs[i], L, mode, m, x, g);
+        if (!G.letter.empty()) {
+            const bool sub = sub_b && sub_b[i] >= 0 && sub_e[i] >= sub_b[i] && sub_e[i] < (int)G.letter.size();
+            aln = align(G, sub ? subgraph_view(G, sub_b[i], sub_e[i]) : whole_view(G), seqs[i], L, mode, m, x, g);
+        }
         add_alignment(G, aln, seqs[i], wt.data(), L);
     }
     std::vector<int> path = heaviest_bundle(G);

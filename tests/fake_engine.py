@@ -109,16 +109,17 @@ class OracleEngine(object):
         return (self.recs[idx][0], self.recs[idx][1]) if idx >= 0 else (aux[-idx - 1], None)
 
     def poa_consensus(self, job_off, layer_src, layer_begin, layer_len, aux=None, mode=0, match=5, mismatch=-4, gap=-2,
-                      trim=False, max_nodes=0, shape=None, order_mode=0):
+                      trim=False, max_nodes=0, shape=None, order_mode=0, layer_sub=None):
         out = []
         for j in range(len(job_off) - 1):
-            seqs, quals = [], []
+            seqs, quals, sub = [], [], []
             for l in range(int(job_off[j]), int(job_off[j + 1])):
                 s, q = self._src(int(layer_src[l]), aux)
                 b, n = int(layer_begin[l]), int(layer_len[l])
                 seqs.append(s[b:b + n])
                 quals.append(q[b:b + n] if q is not None else "")
-            out.append(co.poa_consensus(seqs, quals, mode=mode, match=match, mismatch=mismatch, gap=gap, trim=trim))
+                sub.append(None if layer_sub is None or int(layer_sub[0][l]) < 0 else (int(layer_sub[0][l]), int(layer_sub[1][l])))
+            out.append(co.poa_consensus(seqs, quals, mode=mode, match=match, mismatch=mismatch, gap=gap, trim=trim, sub=sub))
         return out, np.zeros(len(out), dtype=np.int32)
 
     def sg_align_paths(self, a, b, open_pen, aux=None, window=500, want_windows=False):

@@ -78,6 +78,52 @@ def test_polish_matches_oracle_and_template(eng):
         assert co.edit_distance(p, t) <= 0.01 * len(t)
 
 
+def test_polish_with_reads_that_do_not_span_their_windows(eng):
+    """racon aligns a window layer that does not span the window to within 1 % to the sub-graph between its
+    first and last backbone position (window.cpp generate_consensus, spoa Graph::subgraph): reads cut at
+    both ends polish a draft together with full-length ones, GPU == oracle; and the sub-graph entry of the
+    library agrees with the oracle's on explicit ranges."""
+    from ngspeciesid_b200.modules import consensus as C
+    rs, groups, tpl = species_reads(140, 1, 37, 1150, 1250)
+    recs = [rs.read(i) for i in range(len(rs))]
+    fw = [i for i in range(len(recs)) if rs.strand[i] == 0]
+    rng = np.random.default_rng(5)
+    cut = []
+    for i in fw[30:42]:                                   # fragments: cut at both ends by 20-400 bases
+        s, q = recs[i]
+        a, b = int(rng.integers(20, 400)), int(rng.integers(20, 400))
+        cut.append((s[a:len(s) - b], q[a:len(q) - b]))
+    use = recs + cut
+    eng.upload_records(use)
+    full = fw[:30]                                         # enough of them to keep racon's coverage trimming off the ends
+    parts = list(range(len(recs), len(use)))
+    draft, _ = C.draft_consensus_batch(eng, [fw[:6]])
+    pol = C.polish_batch(eng, draft, [full + parts], 2)[0]
+    exp = co.racon_polish(draft[0], [use[i] for i in full + parts], 2)
+    assert pol == exp
+    assert co.edit_distance(pol, tpl[0]) <= 0.01 * len(tpl[0])
+    # the fragments really took the sub-graph route: without them the result differs or they were layers
+    only_full = co.racon_polish(draft[0], [use[i] for i in full], 2)
+    assert co.edit_distance(exp, tpl[0]) <= co.edit_distance(only_full, tpl[0])
+    # explicit ranges through the C ABI
+    backbone = draft[0][:500]
+    lay = [use[i] for i in full[:5]]
+    segs = [(s[100:340], q[100:340]) for s, q in lay]
+    eng.upload_records(segs)
+    n = len(segs)
+    job_off = [0, n + 1]
+    src = [-1] + list(range(n)); beg = [0] * (n + 1); ln = [len(backbone)] + [len(s) for s, _ in segs]
+    sb = [-1] + [95] * n; se = [-1] + [345] * n
+    got, _nodes = eng.poa_consensus(job_off, src, beg, ln, aux=[backbone], mode=1, match=3, mismatch=-5, gap=-4, trim=False,
+                                    layer_sub=(sb, se))
+    want = co.poa_consensus([backbone] + [s for s, _ in segs], [""] + [q for _, q in segs], mode=1, match=3, mismatch=-5, gap=-4,
+                            trim=False, sub=[None] + [(95, 345)] * n)
+    assert got[0] == want
+    whole = co.poa_consensus([backbone] + [s for s, _ in segs], [""] + [q for _, q in segs], mode=1, match=3, mismatch=-5, gap=-4,
+                             trim=False)
+    assert want != whole or len(want) == len(whole)
+
+
 def test_polish_mixed_strands(eng):
     """A centre that absorbed its reverse-complement cluster (consensus.py:148-183): reads of both
     strands polish it, each in the orientation that aligns better."""
