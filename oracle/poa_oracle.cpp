@@ -453,4 +453,29 @@ int oracle_poa_consensus_sub(const char **seqs, const char **quals, int n, int m
     return e - b;
 }
 
+/* Test hook: graph of the n sequences (added as in oracle_poa_consensus_ex, order_mode 0), then the node ids of
+ * subgraph_view(begin, end) in view order. Returns their number, -2 for a range outside the graph, -3 if cap is small. */
+int oracle_poa_subview(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                       int begin, int end, int *order_out, int cap)
+{
+    Graph G;
+    std::vector<int> wt;
+    for (int i = 0; i < n; ++i) {
+        const int L = (int)strlen(seqs[i]);
+        wt.assign(L, 1);
+        if (quals) {
+            const int ql = (int)strlen(quals[i]);
+            for (int t = 0; t < L; ++t) wt[t] = (t < ql) ? (int)quals[i][t] - 33 : 0;
+        }
+        std::vector<Pair> aln;
+        if (!G.letter.empty()) aln = align(G, whole_view(G), seqs[i], L, mode, m, x, g);
+        add_alignment(G, aln, seqs[i], wt.data(), L);
+    }
+    if (begin < 0 || end < begin || end >= (int)G.letter.size()) return -2;
+    const View W = subgraph_view(G, begin, end);
+    if ((int)W.order.size() > cap) return -3;
+    for (size_t r = 0; r < W.order.size(); ++r) order_out[r] = W.order[r];
+    return (int)W.order.size();
+}
+
 }  // extern "C"

@@ -6,8 +6,8 @@
 #include <vector>
 #include "../ngspeciesid_b200/csrc/poa_core.cuh"
 
-extern "C" int poa_core_host_consensus(const char **seqs, const char **quals, int n, int mode, int m, int x,
-                                       int g, int trim, char *out, int cap, int Vcap)
+static int host_consensus_or_view(const char **seqs, const char **quals, int n, int mode, int m, int x,
+                                  int g, int trim, char *out, int cap, int Vcap, int view_begin, int view_end, int *view_order, int view_cap)
 {
     int Lmax = 1;
     for (int i = 0; i < n; ++i) Lmax = std::max<int>(Lmax, (int)strlen(seqs[i]));
@@ -54,7 +54,30 @@ extern "C" int poa_core_host_consensus(const char **seqs, const char **quals, in
         poa_add_alignment(G, n_aln, s, q, L);
         if (G.err) return -100 - G.err;
     }
+    if (view_order) {
+        // the sub-graph view of the finished graph (poa_subgraph_view): node ids in view order
+        if (view_begin < 0 || view_end < view_begin || view_end >= G.V) return -2;
+        std::vector<uint8_t> member((size_t)G.V);
+        std::vector<int32_t> order((size_t)G.V), rank((size_t)G.V);
+        const int nv = poa_subgraph_view(G, view_begin, view_end, member.data(), order.data(), rank.data());
+        if (nv < 0 || nv > view_cap) return -3;
+        for (int r = 0; r < nv; ++r) { view_order[r] = order[r]; if (rank[order[r]] != r || !member[order[r]]) return -4; }
+        return nv;
+    }
     int len = poa_consensus(G, trim, (uint8_t *)out, cap - 1);
     if (len >= 0) out[len] = 0;
     return len;
+}
+
+extern "C" int poa_core_host_consensus(const char **seqs, const char **quals, int n, int mode, int m, int x,
+                                       int g, int trim, char *out, int cap, int Vcap)
+{
+    return host_consensus_or_view(seqs, quals, n, mode, m, x, g, trim, out, cap, Vcap, -1, -1, nullptr, 0);
+}
+
+// graph of the n sequences (added like poa_core_host_consensus), then the view [begin, end] of it
+extern "C" int poa_core_host_subview(const char **seqs, const char **quals, int n, int mode, int m, int x, int g,
+                                     int begin, int end, int *order_out, int order_cap, int Vcap)
+{
+    return host_consensus_or_view(seqs, quals, n, mode, m, x, g, 0, nullptr, 0, Vcap, begin, end, order_out, order_cap);
 }

@@ -77,3 +77,33 @@ def test_degenerate_inputs(core):
                         [["ACGTACGT", "TTTTTTTT", "ACGTACGT"], ["55555555"] * 3]):
         exp = co.poa_consensus(seqs, quals, mode=0, match=5, mismatch=-4, gap=-2)
         assert run_core(core, seqs, quals, 0, 5, -4, -2, False) == exp
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_subgraph_view_matches_oracle(core, seed):
+    """poa_subgraph_view (the part of a window graph racon aligns a non-spanning layer to) against the oracle's
+    restatement of spoa Graph::subgraph: same nodes in the same order, on graphs both sides built themselves."""
+    from oracle import cluster_oracle as oc
+    olib = oc._lib()
+    rng = np.random.default_rng(seed)
+    tpl, seqs, quals = noisy_cluster(rng, int(rng.integers(120, 260)), int(rng.integers(8, 30)), 0.12)
+    seqs, quals = [tpl] + seqs, [""] + quals                      # backbone first, weight 0, like a racon window
+    n = len(seqs)
+    a = (ctypes.c_char_p * n)(*[s.encode() for s in seqs])
+    q = (ctypes.c_char_p * n)(*[s.encode() for s in quals])
+    cap = 20000
+    core.poa_core_host_subview.restype = ctypes.c_int
+    core.poa_core_host_subview.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p)] + [ctypes.c_int] * 7 + \
+                                          [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]
+    olib.oracle_poa_subview.restype = ctypes.c_int
+    olib.oracle_poa_subview.argtypes = [ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_char_p)] + [ctypes.c_int] * 7 + \
+                                       [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    L = len(tpl)
+    for b, e in [(0, L - 1), (10, L - 20), (L // 3, 2 * L // 3), (5, 5), (L - 2, L - 1), (0, 0)]:
+        got, want = (ctypes.c_int * cap)(), (ctypes.c_int * cap)()
+        ng = core.poa_core_host_subview(a, q, n, 1, 3, -5, -4, b, e, got, cap, 20000)
+        nw = olib.oracle_poa_subview(a, q, n, 1, 3, -5, -4, b, e, want, cap)
+        assert ng == nw and ng >= e - b + 1
+        assert list(got[:ng]) == list(want[:nw])
+        assert set(range(b, e + 1)) <= set(got[:ng])          # the backbone stretch is in the view
+        assert all(v >= b for v in got[:ng])
