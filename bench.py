@@ -269,7 +269,7 @@ def run_ours(args):
         import copy
         a3 = copy.copy(args)
         a3.config, a3.steps, a3.warmup = "c3", max(1, min(args.steps, 3)), max(1, min(args.warmup, 2))
-        a3.no_roofline = a3.no_cpu = a3.no_modules = True
+        a3.no_roofline = a3.no_cpu = a3.no_modules = a3.no_concurrent = True
         a3.reads = 0
         r3 = _measure(a3, pick_config(a3, world), env)
         if rank == 0:
@@ -422,6 +422,12 @@ def _measure(args, cfg, env):
         if st["align_cells"] and dev["k4"] > 0:
             result["k4_gcups_rank0"] = st["align_cells"] * args.steps / (dev["k4"] / 1000.0) / 1e9
 
+    # ---- independent batches in flight on one GPU (what `--t N` on one GPU does, modules/parallelize.py; the
+    # headline above stays one pass at a time so that it is the same quantity at every N)
+    if rank == 0 and world == 1 and not args.no_concurrent:
+        result["concurrent_batches"] = concurrent_leg(E, M, local, K, W, max_gap, (h_seq, h_qual, h_off), my_acc, my_scores,
+                                                      n_total, args, mg)
+
     # ---- consensus of the FINAL clusters (NGSpeciesID:124-158), clusters sharded over the ranks
     if not args.no_consensus:
         pipe.phase = {}
@@ -558,6 +564,41 @@ def workload_config(cfg, world):
                   % (cfg["reads_per_gpu"] * (750 * 2.25 + 119 * 8) / 1e6)}
 
 
+def concurrent_leg(E, M, device, k, w, max_gap, up, accs, scores, n_total, args, mg):
+    """Throughput with 2 and 3 independent passes in flight on the one GPU: every lane is a host thread with its own
+    engine (context + stream) running the same step as the headline (K1 + K0 + greedy pass on its resident batch)."""
+    import threading
+    lanes_max = 3
+    engs = [E.Engine(device) for _ in range(lanes_max)]
+    pipes = [M.Pipeline(e, mg, None, None, rank=0, world=1, k=k, w=w) for e in engs]
+    for e, p in zip(engs, pipes):
+        e.upload(*up)
+        p.cluster(max_gap, accs, scores, 0, n_total, tile_reads=args.tile)
+    steps = max(2, args.steps // 2)
+    out = {"metric": "reads/s with independent batches in flight on one GPU (one host thread, context and stream per batch)",
+           "unit": "reads/s", "steps_per_lane": steps}
+
+    def run(n_lanes):
+        def work(p):
+            for _ in range(steps):
+                p.cluster(max_gap, accs, scores, 0, n_total, tile_reads=args.tile)
+            p.eng.sync()
+        th = [threading.Thread(target=work, args=(pipes[i],)) for i in range(n_lanes)]
+        t = time.perf_counter()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        return time.perf_counter() - t
+    for n_lanes in (1, 2, 3):
+        run(n_lanes) if n_lanes > 1 else None                       # warm-up of the combination
+        dt = run(n_lanes)
+        out[str(n_lanes)] = n_total * steps * n_lanes / dt
+    for e in engs:
+        e.close()
+    return out
+
+
 def _consensus_cpu_worker(job):
     from oracle import consensus_oracle as co
     recs, iters = job
@@ -669,6 +710,7 @@ def main():
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
     ap.add_argument("--no-consensus", dest="no_consensus", action="store_true")
     ap.add_argument("--no-modules", dest="no_modules", action="store_true")
+    ap.add_argument("--no-concurrent", dest="no_concurrent", action="store_true", help="skip the batches-in-flight leg (N = 1)")
     ap.add_argument("--no-north-star", dest="no_north_star", action="store_true", help="N = 8: skip the configs[3] run")
     ap.add_argument("--force-north-star", dest="force_north_star", action="store_true",
                     help="run the nested configs[3] workload (125 k reads per GPU) at any N: a dry run of the N = 8 path")

@@ -4,6 +4,7 @@ end to end (host numpy buffers in, host numpy results out) and what the referenc
 wrappers in ngspeciesid_b200.modules sit on.
 """
 import ctypes
+import threading
 import math
 
 import numpy as np
@@ -437,13 +438,26 @@ def nccl_unique_id():
 
 
 _ENGINES = {}
+_ENGINES_LOCK = threading.Lock()
+_TLS = threading.local()
 
 
-def get_engine(device=0):
-    """One cached Engine per device for the reference-shaped wrappers."""
-    e = _ENGINES.get(device)
-    if e is None or e.h is None:
-        e = _ENGINES[device] = Engine(device)
+def set_engine_slot(slot):
+    """Engine slot of the calling thread: threads that run independent batches on one GPU at the same time
+    (modules.parallelize.parallel_clustering) each work on their own context and stream."""
+    _TLS.slot = int(slot)
+
+
+def get_engine(device=0, slot=None):
+    """One cached Engine per (device, slot) for the reference-shaped wrappers; slot defaults to the calling
+    thread's (0 unless set_engine_slot was called)."""
+    if slot is None:
+        slot = getattr(_TLS, "slot", 0)
+    key = (device, slot)
+    with _ENGINES_LOCK:
+        e = _ENGINES.get(key)
+        if e is None or e.h is None:
+            e = _ENGINES[key] = Engine(device)
     return e
 
 
