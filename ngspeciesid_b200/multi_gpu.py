@@ -241,40 +241,67 @@ class Pipeline(object):
             if then_prefetch is not None:
                 self.prefetch(then_prefetch, delay=self._pf_delay)
             t = self._tick("start_prefetch", t)
-        eng, mg = self.eng, self.mg
-        if upload is not None and not prefetched:
+        L = self.local_pass(self.eng, max_gap, accs, scores, gid0, upload=None if prefetched else upload,
+                            tile_reads=tile_reads, phase=self.phase)
+        self._pf_delay = 0.35 * L["t_pass"]
+        return self.exchange_and_merge(L, max_gap, n_total)
+
+    def local_pass(self, eng, max_gap, accs, scores, gid0, upload=None, tile_reads=0, phase=None):
+        """This rank's batch on `eng`, no communication: (upload,) K1 minimizers, K0 quality statistics, the
+        greedy pass; then the plan of its survivors. Returns the record `exchange_and_merge` takes. May run on
+        a host thread of its own (cluster_stream): it touches `eng` and the given phase dict only."""
+        phase = self.phase if phase is None else phase
+
+        def tick(name, t0):
+            eng.sync()
+            phase[name] = phase.get(name, 0.0) + (time.perf_counter() - t0)
+            return time.perf_counter()
+        t = time.perf_counter()
+        if upload is not None:
             eng.upload(*upload)
-            t = self._tick("upload", t)
+            t = tick("upload", t)
         eng.minimizers(self.k, self.w)
         eng.quality_stats()
-        t = self._tick("k1_k0", t)
+        t = tick("k1_k0", t)
         n = len(accs)
         if getattr(self, "_acc_rank_for", None) is not accs:
             self._acc_rank, self._acc_rank_for = E.accession_ranks(accs), accs
         assign, via, st = eng.cluster(self.k, self.w, max_gap, np.arange(n, dtype=np.int32), self._acc_rank,
                                       tile_reads=tile_reads, **self.kw)
-        self.local_assign, self.local_stats = assign, st
         t_pass = time.perf_counter() - t
-        t = self._tick("cluster_local", t)
-        self._pf_delay = 0.35 * t_pass
+        t = tick("cluster_local", t)
         reps = np.nonzero(assign == -1)[0].astype(np.int32)
         rep_of = np.where(assign >= 0, assign, np.arange(n))
         rep_of[assign == -2] = -1
         size0_local = np.bincount(rep_of[rep_of >= 0], minlength=n)[reps]
-        # ---- exchange: plans over the host all-gather, representatives device to device
         blob = pack_rep_tags([gid0 + int(r) for r in reps], [scores[r] for r in reps], size0_local, [accs[r] for r in reps])
+        dev = {}
+        if hasattr(eng, "phase_ms"):                     # device timers of this pass (stand-in engines of the CPU tests have none)
+            dev = {"k1": eng.phase_ms(1), "k0": eng.phase_ms(2), "cluster": eng.phase_ms(3), "k4": eng.phase_ms(4), "map": eng.phase_ms(5)}
+        return {"eng": eng, "n": n, "assign": assign, "stats": st, "reps": reps, "rep_of": rep_of, "blob": blob,
+                "t_pass": t_pass, "device_ms": dev}
+
+    def exchange_and_merge(self, L, max_gap, n_total):
+        """The communication half of a step for the local result L: plans over the host all-gather, the survivors
+        device to device into `mg`, the merge rounds (pairs of a round on different ranks), the final root of every
+        local read. All collectives of a step are issued here, by the calling thread, in the same order on every rank."""
+        eng, mg = L["eng"], self.mg
+        n, reps, rep_of = L["n"], L["reps"], L["rep_of"]
+        self.eng = eng                                   # the engine that holds this step's batch (consensus reads from it)
+        self.local_assign, self.local_stats = L["assign"], L["stats"]
+        t = time.perf_counter()
         if self.world > 1:
-            blobs = eng.allgather_bytes(blob)
+            blobs = eng.allgather_bytes(L["blob"])
             counts = eng.gather_representatives(reps, mg)
         else:
             # one rank: there is no merge round, nothing ever reads a gathered copy of the representatives
-            blobs, counts = [blob], np.array([len(reps)], dtype=np.int64)
+            blobs, counts = [L["blob"]], np.array([len(reps)], dtype=np.int64)
         t = self._tick("gather_representatives", t)
         gids, gscores, gsizes, gaccs = [], [], [], []
-        for b in blobs:
-            a, s, z, c = unpack_rep_tags(b)
-            gids += a; gscores += s; gsizes += z; gaccs += c
-        assert [len(unpack_rep_tags(b)[0]) for b in blobs] == [int(c) for c in counts]
+        for b_ in blobs:
+            a_, s_, z_, c_ = unpack_rep_tags(b_)
+            gids += a_; gscores += s_; gsizes += z_; gaccs += c_
+        assert [len(unpack_rep_tags(b_)[0]) for b_ in blobs] == [int(c_) for c_ in counts]
         self.g_gid, self.g_score, self.g_size0, self.g_acc = gids, gscores, gsizes, gaccs
         self.g_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         ms = MergeState(counts)
@@ -283,13 +310,13 @@ class Pipeline(object):
         while not ms.done():
             pairs = ms.pairs()
             dec = np.full(ms.R, INT32_MIN, dtype=np.int32)
-            todo = [p for p in pairs if p[2]]
+            todo = [p_ for p_ in pairs if p_[2]]
             for pj, (_nb, lo, hi) in enumerate(todo):
                 if pj % self.world != self.rank:
                     continue
-                a, _v, _s = mg.cluster(self.k, self.w, max_gap, np.asarray(hi, dtype=np.int32), g_rank,
-                                       init_reps=np.asarray(lo, dtype=np.int32), **self.kw)
-                dec[np.asarray(hi)] = np.where(a >= 0, a, -1)
+                a_, _v, _s = mg.cluster(self.k, self.w, max_gap, np.asarray(hi, dtype=np.int32), g_rank,
+                                        init_reps=np.asarray(lo, dtype=np.int32), **self.kw)
+                dec[np.asarray(hi)] = np.where(a_ >= 0, a_, -1)
             eng.allreduce(dec, "max")
             ms.apply(pairs, dec)
             rounds += 1
@@ -313,6 +340,47 @@ class Pipeline(object):
         out[ok] = np.asarray(gids, dtype=np.int64)[root_of_g[g_of_local[rep_of[ok]]]]
         self.n_total = n_total
         return out
+
+    def cluster_stream(self, n_steps, max_gap, accs, scores, gid0, n_total, upload=None, tile_reads=0, on_step=None):
+        """n_steps batches one after the other with the two halves of a step overlapped: the local pass of step
+        s + 1 runs on the alternate batch engine, driven by a second host thread, while this thread does the
+        exchange and the merge rounds of step s (and waits there for slower ranks). The second thread issues no
+        collective. upload = (seq, qual, offsets) fed to every step (end to end), or None when BOTH batch engines
+        hold the batch already. on_step(step, roots, local_record) is called after every step.
+        Returns the roots of the last step; `self.eng` is then the engine that holds its batch."""
+        import queue
+        if self.alt is None:
+            raise RuntimeError("cluster_stream needs an alternate engine")
+        engs = [self.eng, self.alt]
+        free = [threading.Semaphore(1), threading.Semaphore(1)]
+        q = queue.Queue()
+        wphase = {}
+
+        def worker():
+            try:
+                for s_ in range(n_steps):
+                    free[s_ & 1].acquire()
+                    q.put(self.local_pass(engs[s_ & 1], max_gap, accs, scores, gid0, upload=upload, tile_reads=tile_reads, phase=wphase))
+            except BaseException as exc:                 # surfaces in the calling thread
+                q.put(exc)
+        th = threading.Thread(target=worker, daemon=True)
+        th.start()
+        roots = None
+        for s_ in range(n_steps):
+            t = time.perf_counter()
+            L = q.get()
+            if isinstance(L, BaseException):
+                raise L
+            self.phase["wait_local_pass"] = self.phase.get("wait_local_pass", 0.0) + (time.perf_counter() - t)
+            roots = self.exchange_and_merge(L, max_gap, n_total)
+            free[s_ & 1].release()
+            if on_step is not None:
+                on_step(s_, roots, L)
+        th.join()
+        for k_, v_ in wphase.items():
+            self.phase[k_] = self.phase.get(k_, 0.0) + v_
+        self.alt = engs[0] if self.eng is engs[1] else engs[1]
+        return roots
 
     # ---- consensus on the final clusters -----------------------------------------------------------
     def consensus(self, abundance_ratio, max_seqs, racon_iter, rc_identity_threshold=0.9):
