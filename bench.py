@@ -18,7 +18,9 @@ Workloads (config.workload names the one that ran):
 One "step" = one pass of the clustering hot path over the whole batch of every rank: K1 minimizers
 + K0 quality statistics + the greedy pass (K2/K3 mapping, K4 block alignment) and, for N > 1, the
 NCCL gather of the surviving representatives + the log2(N) merge rounds.
-  value   : reads/s with the reads resident in HBM, wall clock between device syncs, max over ranks
+  value   : reads/s with the reads resident in HBM, wall clock over all K steps between device syncs, max over
+            ranks; the local pass of step s + 1 overlaps the exchange + merge rounds of step s
+            (Pipeline.cluster_stream: second batch engine, second host thread, collectives on one thread)
   e2e     : the same from pinned host buffers (H2D of bases + qualities inside the timed region,
             D2H of the assignments), input double-buffered: the transfer of step n+1 runs on a second
             engine under the clustering pass of step n (Pipeline.prefetch)

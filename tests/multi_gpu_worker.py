@@ -48,6 +48,19 @@ def main():
     pipe = M.Pipeline(*engs, rank=rank, world=world, k=args.k, w=args.w)
     roots = pipe.cluster(E.max_gap_table(p_emp, args.min_prob_no_hits), [r[2] for r in mine], [r[5] for r in mine],
                          lo, len(ra))
+    # the same steps through cluster_stream (local pass of step s + 1 on a second batch engine and host thread under
+    # the exchange + merge rounds of step s): same roots, and the state of the last step feeds the consensus below
+    if on_gpu:
+        alt = E.Engine(dev)
+        if world > 1:
+            alt.nccl_share(engs[0])
+    else:
+        alt = OracleEngine(p_emp, args, ops)
+    alt.upload_records([(r[3], r[4]) for r in mine])
+    pipe.alt = alt
+    roots_s = pipe.cluster_stream(3, E.max_gap_table(p_emp, args.min_prob_no_hits), [r[2] for r in mine], [r[5] for r in mine],
+                                  lo, len(ra))
+    assert [int(x) for x in roots_s] == [int(x) for x in roots], "cluster_stream differs from cluster"
     # member lists of the local round-0 clusters (global ids), for the concatenation order
     local = {}
     for i, rp in enumerate(pipe.local_rep_of):
