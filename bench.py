@@ -344,8 +344,18 @@ def _measure(args, cfg, env):
         for k_ in dev:
             dev[k_] += L["device_ms"][k_]
 
+    # Overlapped steps pay while the merge phase is short: measured 33.3 vs 34.6 ms per step at N = 2, 39.4 vs 41 at
+    # N = 4, but 50.6 vs <= 49.7 at N = 8, where a rank spends ~8 ms per step inside the collectives of three merge
+    # rounds and its spinning NCCL kernels slow the local pass that runs next to them.
+    use_stream = world <= 4 and not args.no_stream
+
     def resident_loop(n):
-        pipe.cluster_stream(n, max_gap, my_acc, my_scores, lo, n_total, upload=None, tile_reads=args.tile, on_step=on_step)
+        if use_stream:
+            pipe.cluster_stream(n, max_gap, my_acc, my_scores, lo, n_total, upload=None, tile_reads=args.tile, on_step=on_step)
+        else:
+            for s_ in range(n):
+                roots = pipe.cluster(max_gap, my_acc, my_scores, lo, n_total, tile_reads=args.tile)
+                on_step(s_, roots, pipe.last_local)
 
     resident_loop(max(2, args.warmup))
     sampler = ClockSampler(local) if rank == 0 else None
@@ -418,8 +428,12 @@ def _measure(args, cfg, env):
             "vs_baseline": None, "dtype": "u32/int32 (f64 for error rates)", "data": "synthetic",
             "config": workload_config(cfg, world),
             "timing": "wall clock between device syncs over all K steps, max over ranks (the host orchestrates the greedy pass); "
-                      "the local pass of step s + 1 overlaps the exchange + merge rounds of step s (Pipeline.cluster_stream); "
-                      "per-phase milliseconds per step as max/min over ranks in `phases` (they overlap: their sum exceeds ms_per_step)",
+                      + ("the local pass of step s + 1 overlaps the exchange + merge rounds of step s (Pipeline.cluster_stream); "
+                         "per-phase milliseconds per step as max/min over ranks in `phases` (they overlap: their sum exceeds ms_per_step)"
+                         if use_stream else
+                         "one step after the other (N >= 8: overlapped steps measured slower); per-phase milliseconds per step as "
+                         "max/min over ranks in `phases`"),
+            "steps_overlapped": bool(use_stream),
             "phases": phases,
             "e2e": {"value": e2e_v, "unit": "reads/s",
                     "h2d_bytes_per_step": int(offsets[-1]) * 2 + 8 * (n_total + world) + 8 * n_total,
@@ -720,6 +734,8 @@ def main():
     ap.add_argument("--no-consensus", dest="no_consensus", action="store_true")
     ap.add_argument("--no-modules", dest="no_modules", action="store_true")
     ap.add_argument("--no-concurrent", dest="no_concurrent", action="store_true", help="skip the batches-in-flight leg (N = 1)")
+    ap.add_argument("--no-stream", dest="no_stream", action="store_true",
+                    help="one step after the other instead of Pipeline.cluster_stream (the default from N = 8 on)")
     ap.add_argument("--no-north-star", dest="no_north_star", action="store_true", help="N = 8: skip the configs[3] run")
     ap.add_argument("--force-north-star", dest="force_north_star", action="store_true",
                     help="run the nested configs[3] workload (125 k reads per GPU) at any N: a dry run of the N = 8 path")

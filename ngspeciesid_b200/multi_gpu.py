@@ -244,6 +244,7 @@ class Pipeline(object):
         L = self.local_pass(self.eng, max_gap, accs, scores, gid0, upload=None if prefetched else upload,
                             tile_reads=tile_reads, phase=self.phase)
         self._pf_delay = 0.35 * L["t_pass"]
+        self.last_local = L                              # record of the local half (device timers, stats) of this step
         return self.exchange_and_merge(L, max_gap, n_total)
 
     def local_pass(self, eng, max_gap, accs, scores, gid0, upload=None, tile_reads=0, phase=None):
